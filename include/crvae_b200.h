@@ -1,0 +1,183 @@
+/*
+ * crvae_b200.h -- C ABI of libcrvae_b200.so: the B200 (sm_100a) kernels behind the CR-VAE training
+ * hot path of anonyme-Zheng/VAE-connexe (reference file: CRVAE_lorenz96.py).
+ *
+ * The reference has no FFI of its own (it is pure Python on top of torch.nn.GRU / nn.Linear /
+ * autograd); the drop-in boundary is its Python symbol surface (CRVAE, VRAE4E, GC(), prox_update,
+ * train_phase1/2 ...), mirrored by the package vae-connexe_b200/.  This header is the layer below
+ * that mirror: plain device pointers + sizes + a cudaStream_t passed as void*; no torch types.
+ * Each entry point cites the reference statement(s) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated otherwise; all tensors are dense
+ *     row-major with the index order written in the comment;
+ *   - H (hidden) must be 64 (the only size any reference driver uses, CRVAE_lorenz96.py:768);
+ *     G = 3H = 192 gate rows ordered [r; z; n] as in nn.GRU.weight_*;
+ *   - P = heads in this call (a head shard on multi-GPU), T = timesteps, B = batch rows,
+ *     K = projection depth (= number of series p);
+ *   - return value: 0 on success, otherwise a negative CRVAE_E_* code or a positive cudaError_t;
+ *     crvae_last_error() returns a static description for the calling thread;
+ *   - every call is asynchronous on `stream`; nothing synchronises; no global state is kept
+ *     (besides the launch counter below).  Re-entrant for distinct streams/buffers.
+ */
+#ifndef CRVAE_B200_H
+#define CRVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRVAE_ABI_VERSION 1
+#define CRVAE_HIDDEN 64
+
+#define CRVAE_E_BADARG   (-1)   /* unsupported size / null pointer / misaligned buffer */
+#define CRVAE_E_NODEVICE (-2)   /* no sm_100 device available */
+
+/* GEMM operand forms for crvae_gemm_f32 */
+#define CRVAE_GEMM_NT 0   /* C[m,n] = sum_k A[m,k] * B[n,k]   (F.linear: x @ W^T)          */
+#define CRVAE_GEMM_TN 1   /* C[m,n] = sum_k A[k,m] * B[k,n]   (weight gradient: dY^T @ X)  */
+#define CRVAE_GEMM_NN 2   /* C[m,n] = sum_k A[m,k] * B[k,n]   (input gradient: dY @ W)     */
+
+/* KL forms for crvae_latent_fwd / crvae_latent_bwd */
+#define CRVAE_KL_STANDARD 0 /* -0.5*sum(1 + log_var - mu^2 - exp(log_var))                        */
+#define CRVAE_KL_SWAPPED  1 /* what the reference trainers evaluate: forward returns
+                               (pred, log_var, mu) (CRVAE_lorenz96.py:221) but the trainer unpacks
+                               (pred, mu, log_var) (:482,:508), so the roles are exchanged:
+                               -0.5*sum(1 + mu - log_var^2 - exp(mu))                             */
+
+int         crvae_abi_version(void);
+const char* crvae_last_error(void);
+/* number of kernel launches issued through this library since load / last reset */
+uint64_t    crvae_launch_count(void);
+void        crvae_launch_count_reset(void);
+/* 0 when the current device is compute capability 10.x, else CRVAE_E_NODEVICE */
+int         crvae_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched fp32 GEMM (exact FFMA path).  Replaces the ATen `addmm`/`mm` calls under nn.GRU's
+ * input projection (CRVAE_lorenz96.py:119, :208), nn.Linear (:210-211) and their autograd twins.
+ *   C[b] (M x N, ldc) = op(A[b]) * op(B[b]) (+ bias[b][n])        b = 0..batch-1
+ * strides sA/sB/sC/sBias are in elements and may be 0 (operand shared by all batches).
+ * accumulate != 0 adds into C instead of overwriting.
+ * ------------------------------------------------------------------------------------------- */
+int crvae_gemm_f32(int form, int batch, int M, int N, int K,
+                   const float* A, int lda, int64_t sA,
+                   const float* B, int ldb, int64_t sB,
+                   float* C, int ldc, int64_t sC,
+                   const float* bias, int64_t sBias,
+                   int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head input projection  (nn.GRU's `linear_ih` for all heads and timesteps at once;
+ * GRU.forward, CRVAE_lorenz96.py:115-119).
+ *   gates[i][t][b][:] = b_ih[i][:] + x[t][b][:] . w_ih[i]^T          for t >= t_skip
+ * x [T,B,K]; w_ih [P,G,K] (masked-dense: structural zeros for unconnected inputs);
+ * b_ih [P,G]; gates [P,T,B,G].  Steps t < t_skip are known-zero inputs (the prepended zero
+ * step, :205/:119) and are not written: crvae_gru_fwd substitutes b_ih for them.
+ * ------------------------------------------------------------------------------------------- */
+int crvae_proj_fwd(const float* x, const float* w_ih, const float* b_ih, float* gates,
+                   int P, int T, int B, int K, int t_skip, void* stream);
+
+/* Weight gradient of the projection (autograd of the above, :497):
+ *   dw_ih[i] (G x K) = sum_{t>=t_skip,b} dgates[i][t][b][:]^T x[t][b][:]   (x mask[i][k] if mask)
+ * workspace: >= crvae_proj_wgrad_workspace(P,T,B,K) bytes (split-reduction partials).          */
+size_t crvae_proj_wgrad_workspace(int P, int T, int B, int K);
+int crvae_proj_wgrad(const float* dgates, const float* x, const uint8_t* mask, float* dw_ih,
+                     int P, int T, int B, int K, int t_skip, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Persistent multi-head GRU recurrence, forward (ATen's per-step `linear_hh` + gate math under
+ * nn.GRU, :119/:208, fused with the per-head Linear(H,1), :120).
+ *   for t: gh = h W_hh^T + b_hh; r = sig(gi_r+gh_r); z = sig(gi_z+gh_z);
+ *          n = tanh(gi_n + r*gh_n); h = (h - n)*z + n          (this operation order)
+ * gates [P,T,B,G]  in: gi (steps < t_skip: ignored, b_ih used)   out: r | z | n  (in place)
+ * h0 [B,H] shared by all heads (h0_head_stride = 0) or [P,B,H] (h0_head_stride = B*H)
+ * hs [P,T,B,H] = h_1..h_T;  ghn [P,T,B,H] = gh_n (kept for the backward);
+ * pred [P,T,B] = h_t . w_lin[i] + b_lin[i]   (w_lin/b_lin/pred may be NULL: encoder GRU).
+ * ------------------------------------------------------------------------------------------- */
+int crvae_gru_fwd(float* gates, const float* b_ih, const float* w_hh, const float* b_hh,
+                  const float* h0, int64_t h0_head_stride,
+                  const float* w_lin, const float* b_lin,
+                  float* hs, float* ghn, float* pred,
+                  int P, int T, int B, int t_skip, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hand-written BPTT for the above (replaces autograd through :119-:120, triggered at :497).
+ * gates [P,T,B,G]  in: r | z | n   out: dgi = [da_r | da_z | da_n]  (in place)
+ * dpred [P,T,B] (NULL if no output head);  dh_last [P,B,H] gradient flowing into h_T (NULL = 0);
+ * dhs [P,T,B,H] extra gradient w.r.t. every h_t (NULL = 0; VRAE4E's Linear(H,p) head, :167)
+ * outputs: dw_hh [P,G,H], db_hh [P,G], db_ih [P,G], dw_lin [P,H], db_lin [P] (NULL ok with
+ *          w_lin NULL), dh0 [P,B,H].   workspace >= crvae_gru_bwd_workspace(P,B) bytes.
+ * ------------------------------------------------------------------------------------------- */
+size_t crvae_gru_bwd_workspace(int P, int B);
+int crvae_gru_bwd(float* gates, const float* ghn, const float* hs,
+                  const float* h0, int64_t h0_head_stride,
+                  const float* w_hh, const float* w_lin,
+                  const float* dpred, const float* dh_last, const float* dhs,
+                  float* dw_hh, float* db_hh, float* db_ih, float* dw_lin, float* db_lin,
+                  float* dh0, int P, int T, int B, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused reparameterisation + KL  (CRVAE.forward :210-216, VRAE4E.forward :157-163, trainer :486)
+ *   lat [B,2H] = [mu | log_var] (output of the fc_mu|fc_std GEMM);  eps [B,H] ~ N(0,1)
+ *   z [B,H] = mu + exp(0.5*log_var)*eps
+ *   kl_out[0] = mean_b sum_h KL-term (form: CRVAE_KL_*)                 (single deterministic sum)
+ * ------------------------------------------------------------------------------------------- */
+int crvae_latent_fwd(const float* lat, const float* eps, float* z, float* kl_out,
+                     int B, int kl_form, void* stream);
+
+/* Backward of the above + the sum over heads of dh0 (every head's h0 is z, :218):
+ *   dz[b][h] = sum_{i<P} dh0[i][b][h]  (+ dz_extra[b][h] if not NULL; a peer-reduced partial)
+ *   dlat[b][0:H]  = dz + beta * dKL/dmu ;  dlat[b][H:2H] = dz*eps*0.5*exp(0.5*log_var) + beta * dKL/dlog_var
+ * dh0 may be NULL with P = 0 (then dz = dz_extra).  dz_out (NULL ok) receives the head sum.     */
+int crvae_latent_bwd(const float* dh0, int P, const float* dz_extra, const float* lat,
+                     const float* eps, float beta, int kl_form, float* dlat, float* dz_out,
+                     int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused MSE loss forward + backward for all heads (trainer :484, :509; nn.MSELoss 'mean'):
+ *   sse[i]         = sum_{t,b} (pred[i][t][b] - target[i][t][b])^2     (loss = sum_i sse[i]/(T*B))
+ *   dpred[i][t][b] = 2*(pred - target)/(T*B)
+ *   err[i][t][b]   = target - pred          (NULL ok; the phase-2 residual, :599/:639)
+ * pred, target, dpred, err [P,T,B]; target is X[:, 10:, i] of the fixed batch, head-major.
+ * ------------------------------------------------------------------------------------------- */
+int crvae_mse_fwd_bwd(const float* pred, const float* target, float* sse, float* dpred, float* err,
+                      int P, int T, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Plain gradient step  theta <- theta - lr*grad  (:498-499), product rounded to fp32 first as
+ * torch does (`lr * param.grad` then `-=`), no FMA contraction.
+ * ------------------------------------------------------------------------------------------- */
+int crvae_gd_step(float* theta, const float* grad, int64_t n, float lr, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused gradient step + group-lasso proximal update + GC norms on the first-layer weights
+ * (:498-499 restricted to weight_ih_l0, then prox_update :308-314, then what GC() :297 reads):
+ *   W <- W - lr*dW ;  nu_j = ||W[:,j]||_2 ;  W[:,j] <- (W[:,j] / max(nu_j, thr)) * max(nu_j - thr, 0)
+ *   col_norm[i][j] = || updated W[i][:,j] ||_2          (thr = fp32(lam*lr); lam == 0: no prox)
+ * w_ih, dw_ih [P,G,K]; mask [P,K] u8 or NULL (masked-out columns stay exactly 0).
+ * dw_ih may be NULL (prox only, the stand-alone prox_update()).
+ * ------------------------------------------------------------------------------------------- */
+int crvae_gd_prox_gc(float* w_ih, const float* dw_ih, const uint8_t* mask, float* col_norm,
+                     int P, int K, float lr, float thr, int do_prox, void* stream);
+
+/* Adam step with torch.optim.Adam default semantics (:565, :612-614); step counts from 1.       */
+int crvae_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    double lr, double beta1, double beta2, double eps, int step, void* stream);
+
+/* Ridge penalty pieces (ridge_regularize :321-325): out[0] = sum(x^2) over n elements.          */
+int crvae_sumsq(const float* x, int64_t n, float* out, void* stream);
+/* out[0] = sum_i scale[i] * x[i] for n <= 4096 values (loss = sum_i sse[i]/(T*B) and friends)     */
+int crvae_dot_small(const float* x, int n, float scale, float* out, void* stream);
+/* test / tuning hook: force the recurrent kernels' batch tile (16, 32 or 64 rows; 0 = heuristic) */
+void crvae_debug_set_batch_tile(int rows);
+/* grad += 2*lam_ridge*theta (gradient of the ridge term in `smooth`, :488/:513-515)             */
+int crvae_axpy(float* y, const float* x, int64_t n, float alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRVAE_B200_H */

@@ -1,0 +1,298 @@
+// Memory-bound kernels of the CR-VAE hot path: fused reparameterisation + KL, fused MSE
+// forward/backward, gradient step, fused GD + group-lasso prox + GC norms, Adam.
+// All reductions are fixed-order (deterministic); nothing here uses atomics.
+#include "common.cuh"
+
+namespace crvae {
+
+constexpr int H = CRVAE_HIDDEN;
+constexpr int G = CRVAE_G;
+
+// block-wide sum of doubles, fixed order; result valid in every thread
+__device__ double block_sum(double v, double* sh /* >= 32 doubles */) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s += sh[i];
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// z = mu + exp(0.5*log_var)*eps ; KL (CRVAE.forward :210-216, trainer :486)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) latent_fwd_kernel(const float* __restrict__ lat,
+                                                          const float* __restrict__ eps,
+                                                          float* __restrict__ z, float* __restrict__ kl_out,
+                                                          int B, int kl_form) {
+    __shared__ double sh[32];
+    double part = 0.0;
+    const int n = B * H;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        int b = e / H, h = e % H;
+        float mu = lat[b * 2 * H + h], lv = lat[b * 2 * H + H + h];
+        float sigma = expf(__fmul_rn(0.5f, lv));
+        z[e] = __fadd_rn(mu, __fmul_rn(sigma, eps[e]));
+        float term;
+        if (kl_form == CRVAE_KL_SWAPPED) term = 1.f + mu - lv * lv - expf(mu);
+        else term = 1.f + lv - mu * mu - expf(lv);
+        part += (double)(-0.5f * term);
+    }
+    double tot = block_sum(part, sh);
+    if (threadIdx.x == 0) kl_out[0] = (float)(tot / (double)B);
+}
+
+// dz = sum over heads of dh0 (+ peer partial); gradient into [mu | log_var]
+__global__ void latent_bwd_kernel(const float* __restrict__ dh0, int P, const float* __restrict__ dz_extra,
+                                  const float* __restrict__ lat, const float* __restrict__ eps, float beta,
+                                  int kl_form, float* __restrict__ dlat, float* __restrict__ dz_out, int B) {
+    const int n = B * H;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float dz = 0.f;
+    int i = 0;
+    for (; i + 4 <= P; i += 4) {
+        float a0 = dh0[(long long)i * n + e], a1 = dh0[(long long)(i + 1) * n + e];
+        float a2 = dh0[(long long)(i + 2) * n + e], a3 = dh0[(long long)(i + 3) * n + e];
+        dz += a0; dz += a1; dz += a2; dz += a3;     // fixed order
+    }
+    for (; i < P; ++i) dz += dh0[(long long)i * n + e];
+    if (dz_out) dz_out[e] = dz;
+    if (!dlat) return;
+    if (dz_extra) dz += dz_extra[e];
+    const int b = e / H, h = e % H;
+    const float mu = lat[b * 2 * H + h], lv = lat[b * 2 * H + H + h];
+    const float invB = 1.f / (float)B;
+    float dkl_mu, dkl_lv;
+    if (kl_form == CRVAE_KL_SWAPPED) {
+        dkl_mu = -0.5f * (1.f - expf(mu)) * invB;
+        dkl_lv = lv * invB;
+    } else {
+        dkl_mu = mu * invB;
+        dkl_lv = -0.5f * (1.f - expf(lv)) * invB;
+    }
+    const float sigma = expf(0.5f * lv);
+    dlat[b * 2 * H + h] = dz + beta * dkl_mu;
+    dlat[b * 2 * H + H + h] = dz * eps[e] * 0.5f * sigma + beta * dkl_lv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MSE forward + backward, one CTA per head (trainer :484 / :509, residual :599 / :639)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                  float* __restrict__ sse, float* __restrict__ dpred,
+                                                  float* __restrict__ err, int n) {
+    __shared__ double sh[32];
+    const long long base = (long long)blockIdx.x * n;
+    const float scale = 2.f / (float)n;
+    double part = 0.0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        float p = pred[base + e], t = target[base + e];
+        float d = p - t;
+        part += (double)d * (double)d;
+        if (dpred) dpred[base + e] = scale * d;
+        if (err) err[base + e] = t - p;
+    }
+    double tot = block_sum(part, sh);
+    if (threadIdx.x == 0) sse[blockIdx.x] = (float)tot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// theta <- theta - lr*grad (:498-499); the product is rounded before the subtraction, as torch does
+// ---------------------------------------------------------------------------------------------
+__global__ void gd_step_kernel(float* __restrict__ theta, const float* __restrict__ grad, long long n, float lr) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        theta[e] = __fsub_rn(theta[e], __fmul_rn(lr, grad[e]));
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, long long n, float alpha) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        y[e] = fmaf(alpha, x[e], y[e]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused GD + group-lasso prox + GC norms over w_ih [P,G,K]  (:498-499, prox_update :308-314, GC :297)
+// CTA = 32 columns x 8 row groups of one head; a thread keeps its 24 column entries in registers,
+// so W and dW are each read once and W written once (12 B per element).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gd_prox_gc_kernel(float* __restrict__ w, const float* __restrict__ dw,
+                                                         const uint8_t* __restrict__ mask,
+                                                         float* __restrict__ col_norm, int K, float lr, float thr,
+                                                         int do_prox) {
+    __shared__ double red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int head = blockIdx.y, j = blockIdx.x * 32 + tx;
+    const bool live = j < K;
+    const bool keep = live && (mask == nullptr || mask[(long long)head * K + j] != 0);
+    float v[24];
+    double ss = 0.0;
+#pragma unroll
+    for (int q = 0; q < 24; ++q) {
+        const int g = ty + 8 * q;
+        const long long idx = ((long long)head * G + g) * K + j;
+        float x = 0.f;
+        if (keep) {
+            x = w[idx];
+            if (dw) x = __fsub_rn(x, __fmul_rn(lr, dw[idx]));
+        }
+        v[q] = x;
+        ss += (double)x * (double)x;
+    }
+    red[ty][tx] = ss;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += red[y][tx];
+    float nu = (float)sqrt(tot);
+    if (do_prox) {
+        const float den = fmaxf(nu, thr);
+        const float fac = fmaxf(__fsub_rn(nu, thr), 0.f);
+        ss = 0.0;
+#pragma unroll
+        for (int q = 0; q < 24; ++q) {
+            v[q] = __fmul_rn(__fdiv_rn(v[q], den), fac);
+            ss += (double)v[q] * (double)v[q];
+        }
+        __syncthreads();
+        red[ty][tx] = ss;
+        __syncthreads();
+        tot = 0.0;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) tot += red[y][tx];
+        nu = (float)sqrt(tot);
+    }
+    if (live) {
+#pragma unroll
+        for (int q = 0; q < 24; ++q) {
+            const int g = ty + 8 * q;
+            w[((long long)head * G + g) * K + j] = v[q];
+        }
+        if (ty == 0 && col_norm) col_norm[(long long)head * K + j] = nu;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam, torch.optim.Adam default semantics (:565, :612-614)
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float one_minus_b1, float b2, float one_minus_b2,
+                            float eps, float neg_step_size, float bc2_sqrt) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float g = grad[e];
+        // exp_avg.lerp_(grad, 1-b1): start + w*(end-start) (w < 0.5 branch of ATen's lerp)
+        float mm = __fadd_rn(m[e], __fmul_rn(one_minus_b1, __fsub_rn(g, m[e])));
+        // exp_avg_sq.mul_(b2).addcmul_(grad, grad, value=1-b2)
+        float vv = __fadd_rn(__fmul_rn(v[e], b2), __fmul_rn(__fmul_rn(one_minus_b2, g), g));
+        float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), bc2_sqrt), eps);
+        // param.addcdiv_(exp_avg, denom, value=-step_size): self + (value*t1)/t2, left to right as ATen
+        theta[e] = __fadd_rn(theta[e], __fdiv_rn(__fmul_rn(neg_step_size, mm), denom));
+        m[e] = mm; v[e] = vv;
+    }
+}
+
+__global__ void __launch_bounds__(1024) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+    __shared__ double sh[32];
+    double part = 0.0;
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) part += (double)x[e] * (double)x[e];
+    double tot = block_sum(part, sh);
+    if (threadIdx.x == 0) out[0] = (float)tot;
+}
+
+__global__ void __launch_bounds__(256) dot_small_kernel(const float* __restrict__ x, int n, float scale,
+                                                        float* __restrict__ out) {
+    __shared__ double sh[32];
+    double part = 0.0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) part += (double)x[e];
+    double tot = block_sum(part, sh);
+    if (threadIdx.x == 0) out[0] = (float)(tot * (double)scale);
+}
+
+static inline int grid_for(long long n, int block = 256, int cap = 148 * 8) {
+    long long b = (n + block - 1) / block;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace crvae
+
+using namespace crvae;
+
+extern "C" int crvae_latent_fwd(const float* lat, const float* eps, float* z, float* kl_out, int B,
+                                int kl_form, void* stream) {
+    CRVAE_REQUIRE(lat && eps && z && kl_out && B > 0, "bad argument");
+    latent_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lat, eps, z, kl_out, B, kl_form);
+    return check_launch("latent_fwd_kernel");
+}
+
+extern "C" int crvae_latent_bwd(const float* dh0, int P, const float* dz_extra, const float* lat,
+                                const float* eps, float beta, int kl_form, float* dlat, float* dz_out, int B,
+                                void* stream) {
+    CRVAE_REQUIRE(B > 0 && P >= 0 && (P == 0 || dh0), "bad argument");
+    CRVAE_REQUIRE(dlat == nullptr || (lat && eps), "lat/eps required with dlat");
+    int n = B * H;
+    latent_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dh0, P, dz_extra, lat, eps, beta, kl_form,
+                                                                         dlat, dz_out, B);
+    return check_launch("latent_bwd_kernel");
+}
+
+extern "C" int crvae_mse_fwd_bwd(const float* pred, const float* target, float* sse, float* dpred, float* err,
+                                 int P, int T, int B, void* stream) {
+    CRVAE_REQUIRE(pred && target && sse && P >= 0 && T > 0 && B > 0, "bad argument");
+    if (P == 0) return 0;
+    mse_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(pred, target, sse, dpred, err, T * B);
+    return check_launch("mse_kernel");
+}
+
+extern "C" int crvae_gd_step(float* theta, const float* grad, int64_t n, float lr, void* stream) {
+    CRVAE_REQUIRE(theta && grad && n >= 0, "bad argument");
+    if (n == 0) return 0;
+    gd_step_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(theta, grad, n, lr);
+    return check_launch("gd_step_kernel");
+}
+
+extern "C" int crvae_axpy(float* y, const float* x, int64_t n, float alpha, void* stream) {
+    CRVAE_REQUIRE(y && x && n >= 0, "bad argument");
+    if (n == 0) return 0;
+    axpy_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(y, x, n, alpha);
+    return check_launch("axpy_kernel");
+}
+
+extern "C" int crvae_gd_prox_gc(float* w_ih, const float* dw_ih, const uint8_t* mask, float* col_norm, int P,
+                                int K, float lr, float thr, int do_prox, void* stream) {
+    CRVAE_REQUIRE(w_ih && P >= 0 && K > 0, "bad argument");
+    if (P == 0) return 0;
+    gd_prox_gc_kernel<<<dim3((K + 31) / 32, P), 256, 0, (cudaStream_t)stream>>>(w_ih, dw_ih, mask, col_norm, K, lr,
+                                                                                thr, do_prox);
+    return check_launch("gd_prox_gc_kernel");
+}
+
+extern "C" int crvae_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               double lr, double beta1, double beta2, double eps, int step, void* stream) {
+    CRVAE_REQUIRE(theta && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "bad argument");
+    if (n == 0) return 0;
+    // scalars computed in double exactly as torch/optim/adam.py does, then rounded to fp32 at use
+    double bc1 = 1.0 - pow(beta1, (double)step);
+    double bc2 = 1.0 - pow(beta2, (double)step);
+    double step_size = lr / bc1;
+    double bc2_sqrt = sqrt(bc2);
+    adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(theta, grad, exp_avg, exp_avg_sq, n,
+                                                               (float)(1.0 - beta1), (float)beta2,
+                                                               (float)(1.0 - beta2), (float)eps,
+                                                               (float)(-step_size), (float)bc2_sqrt);
+    return check_launch("adam_kernel");
+}
+
+extern "C" int crvae_sumsq(const float* x, int64_t n, float* out, void* stream) {
+    CRVAE_REQUIRE(x && out && n >= 0, "bad argument");
+    sumsq_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out);
+    return check_launch("sumsq_kernel");
+}
+
+extern "C" int crvae_dot_small(const float* x, int n, float scale, float* out, void* stream) {
+    CRVAE_REQUIRE(x && out && n >= 0 && n <= (1 << 20), "bad argument");
+    dot_small_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, n, scale, out);
+    return check_launch("dot_small_kernel");
+}

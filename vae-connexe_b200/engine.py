@@ -1,0 +1,242 @@
+"""Fused multi-head recurrent engine: the storage and kernel orchestration behind CRVAE / VRAE4E.
+
+All p per-variable decoder GRUs of the reference (`networks[i]`, CRVAE_lorenz96.py:200-201) live in
+ONE set of fused buffers and are advanced by ONE kernel per stage:
+
+  theta / grad arenas (flat fp32, identical layout; snapshot = one device copy):
+    w_ih [P,G,p] | w_hh [P,G,H] | b_ih [P,G] | b_hh [P,G] | w_lin [P,H] | b_lin [P]     heads (shard)
+    enc_w_ih [G,p] | enc_w_hh [G,H] | enc_b_ih [G] | enc_b_hh [G] | lat_w [2H,H] | lat_b [2H]   encoder
+  (lat_w = [fc_mu.weight ; fc_std.weight], so mu|log_var come out of one GEMM)
+
+  activations for a bound batch (B rows):
+    gates [P,Td,B,G]  (gi -> r|z|n -> dgi, reused in place through projection/forward/backward)
+    hs, ghn [P,Td,B,H]; pred, dpred [P,Td,B]; dh0 [P,B,H]; encoder twins with P=1, T=Te.
+
+P is the number of heads THIS rank holds (head shard [head_off, head_off+P) of p); the encoder
+is replicated.  The only data-path collective is the sum over ranks of dz = sum_heads dh0.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+H = 64
+G = 3 * H
+ENC_STEPS = 10   # CRVAE_lorenz96.py:208
+DEC_STEPS = 10   # CRVAE_lorenz96.py:119 / :484 (context 20)
+
+HEAD_FIELDS = ("w_ih", "w_hh", "b_ih", "b_hh", "w_lin", "b_lin")
+ENC_FIELDS = ("enc_w_ih", "enc_w_hh", "enc_b_ih", "enc_b_hh", "lat_w", "lat_b")
+
+
+def _f32(x: float) -> float:
+    return float(np.float32(x))
+
+
+class Arena:
+    """Flat fp32 buffer with named views."""
+
+    def __init__(self, shapes: Dict[str, tuple], device):
+        self.shapes = shapes
+        self.offsets = {}
+        off = 0
+        for k, s in shapes.items():
+            off = (off + 3) // 4 * 4                     # keep every field 16-byte aligned
+            self.offsets[k] = off
+            off += int(np.prod(s))
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.views = {k: self.flat[self.offsets[k]:self.offsets[k] + int(np.prod(s))].view(*s)
+                      for k, s in shapes.items()}
+
+    def __getitem__(self, k):
+        return self.views[k]
+
+    def like(self):
+        return Arena(self.shapes, self.flat.device)
+
+
+class CRVAEEngine:
+    """Kernel-level implementation of CRVAE.forward(mode='train') (:203-221), the trainer's loss
+    (:484-489), backward (:497), GD (:498-499) and prox (:502-504) for a head shard."""
+
+    def __init__(self, p: int, mask: np.ndarray, head_off: int = 0, device="cuda", group=None):
+        self.k = L.kernels()
+        self.p = int(p)
+        self.P = int(mask.shape[0])
+        self.head_off = int(head_off)
+        self.device = torch.device(device)
+        self.group = group
+        assert mask.shape == (self.P, self.p)
+        self.mask_np = np.ascontiguousarray(mask.astype(bool))
+        self.dense = bool(self.mask_np.all())
+        self.mask_u8 = None if self.dense else torch.from_numpy(self.mask_np.astype(np.uint8)).to(self.device)
+        P, p_ = self.P, self.p
+        shapes = {
+            "w_ih": (P, G, p_), "w_hh": (P, G, H), "b_ih": (P, G), "b_hh": (P, G), "w_lin": (P, H), "b_lin": (P,),
+            "enc_w_ih": (G, p_), "enc_w_hh": (G, H), "enc_b_ih": (G,), "enc_b_hh": (G,),
+            "lat_w": (2 * H, H), "lat_b": (2 * H,),
+        }
+        self.theta = Arena(shapes, self.device)
+        self.grad = self.theta.like()
+        self.n_wih = P * G * p_
+        self.rest_off = self.theta.offsets["w_hh"]
+        self.col_norm = torch.zeros(P, p_, dtype=torch.float32, device=self.device)
+        self.B = None
+        self.kl_form = L.KL_SWAPPED
+
+    # ------------------------------------------------------------------ batch binding
+    def bind_batch(self, X: torch.Tensor):
+        """X (B, 20, p) on the device: the (fixed, :470-473) training batch.  Pre-arranges the
+        encoder input X[:,0:10] (:208), decoder input [0, X[:,10:19]] (:119) and the per-head
+        targets X[:,10:,i] (:484) in the time-major layouts the kernels stream."""
+        assert X.dim() == 3 and X.shape[2] == self.p and X.shape[1] == ENC_STEPS + DEC_STEPS
+        X = X.to(self.device, torch.float32)
+        B = X.shape[0]
+        self.enc_in = X[:, :ENC_STEPS].transpose(0, 1).contiguous()                       # [Te,B,p]
+        self.dec_in = torch.cat([torch.zeros_like(X[:, :1]), X[:, ENC_STEPS:-1]], 1).transpose(0, 1).contiguous()
+        lo, hi = self.head_off, self.head_off + self.P
+        self.target = X[:, ENC_STEPS:, lo:hi].permute(2, 1, 0).contiguous()               # [P,Td,B]
+        if self.B != B:
+            self._alloc(B)
+
+    def _alloc(self, B: int):
+        P, dev = self.P, self.device
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.B = B
+        self.gates = z(max(P, 1), DEC_STEPS, B, G)
+        self.hs = z(max(P, 1), DEC_STEPS, B, H)
+        self.ghn = z(max(P, 1), DEC_STEPS, B, H)
+        self.pred = z(max(P, 1), DEC_STEPS, B)
+        self.dpred = z(max(P, 1), DEC_STEPS, B)
+        self.err = z(max(P, 1), DEC_STEPS, B)
+        self.dh0 = z(max(P, 1), B, H)
+        self.sse = z(max(P, 1))
+        self.enc_gates = z(1, ENC_STEPS, B, G)
+        self.enc_hs = z(1, ENC_STEPS, B, H)
+        self.enc_ghn = z(1, ENC_STEPS, B, H)
+        self.enc_dh0 = z(1, B, H)
+        self.h0_zero = z(B, H)
+        self.lat = z(B, 2 * H)
+        self.dlat = z(B, 2 * H)
+        self.zlat = z(B, H)
+        self.eps = z(B, H)
+        self.eps_next = z(B, H)      # staging slot: the next forward's noise (backward still needs self.eps)
+        self.dhT = z(1, B, H)
+        self.dz_part = z(B, H)
+        self.ones_B = torch.ones(B, 1, dtype=torch.float32, device=dev)
+        self.kl = z(1)
+        self.loss = z(1)
+        self.scratch = z(4)
+        k = self.k
+        nbytes = max(k.gru_bwd_workspace(max(P, 1), B), k.gru_bwd_workspace(1, B))
+        self.ws_gru = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)
+        nbytes = max(k.proj_wgrad_workspace(max(P, 1), DEC_STEPS, B, self.p),
+                     k.proj_wgrad_workspace(1, ENC_STEPS, B, self.p))
+        self.ws_wgrad = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, eps: Optional[torch.Tensor] = None, want_err: bool = False):
+        """Everything of :204-221 + :484-486 for the bound batch.  eps (B,H) device tensor (the
+        reference's CPU-generator draw, already uploaded); None = reuse self.eps."""
+        k, th, B, P, p_ = self.k, self.theta, self.B, self.P, self.p
+        if eps is not None:
+            self.eps.copy_(eps.reshape(B, H), non_blocking=True)
+        # encoder GRU (gru_left, :208) -> h_T
+        k.proj_fwd(self.enc_in, th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, ENC_STEPS, B, p_, 0)
+        k.gru_fwd(self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
+                  self.enc_hs, self.enc_ghn, None, 1, ENC_STEPS, B, 0)
+        hT = self.enc_hs[0, ENC_STEPS - 1]
+        # [mu | log_var] = h_T [fc_mu ; fc_std]^T + b (:210-211); z = mu + exp(.5 lv) eps (:213-216); KL (:486)
+        k.gemm(L.GEMM_NT, 1, B, 2 * H, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * H, 0, th["lat_b"], 0)
+        k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, self.kl_form)
+        # decoder heads (:218-219 -> GRU.forward :114-121): projection, recurrence (+Linear), MSE
+        if P > 0:
+            k.proj_fwd(self.dec_in, th["w_ih"], th["b_ih"], self.gates, P, DEC_STEPS, B, p_, 1)
+            k.gru_fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
+                      self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
+            k.mse_fwd_bwd(self.pred, self.target, self.sse, self.dpred, self.err if want_err else None,
+                          P, DEC_STEPS, B)
+            k.dot_small(self.sse, P, 1.0 / (DEC_STEPS * B), self.loss)
+        else:
+            self.loss.zero_()
+
+    def forward_staged(self, want_err: bool = False):
+        """forward() on the noise previously staged in self.eps_next (CUDA-graph friendly: the
+        copy is part of the captured sequence, after the backward that still reads self.eps)."""
+        self.eps.copy_(self.eps_next)
+        self.forward(None, want_err)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, beta: float, lam_ridge: float = 0.0, dlat_extra: Optional[torch.Tensor] = None):
+        """Gradient of smooth = loss + ridge + beta*KL (:489/:515) into the grad arena (:497)."""
+        k, th, g, B, P, p_ = self.k, self.theta, self.grad, self.B, self.P, self.p
+        if P > 0:
+            k.gru_bwd(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
+                      g["w_hh"], g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
+            k.proj_wgrad(self.gates, self.dec_in, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1, self.ws_wgrad)
+            if lam_ridge != 0.0:      # d/dW of lam*(|linear.W|^2 + |W_hh|^2), ridge_regularize :321-325
+                k.axpy(g["w_hh"], th["w_hh"], P * G * H, 2.0 * lam_ridge)
+                k.axpy(g["w_lin"], th["w_lin"], P * H, 2.0 * lam_ridge)
+        # dz = sum over ALL heads of dh0 (every head's h0 is z, :218)
+        if self.group is not None:
+            k.latent_bwd(self.dh0 if P > 0 else None, P, None, None, None, 0.0, self.kl_form, None, self.dz_part, B)
+            torch.distributed.all_reduce(self.dz_part, group=self.group)
+            k.latent_bwd(None, 0, self.dz_part, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+        else:
+            k.latent_bwd(self.dh0, P, None, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+        if dlat_extra is not None:
+            k.axpy(self.dlat, dlat_extra, B * 2 * H, 1.0)
+        hT = self.enc_hs[0, ENC_STEPS - 1]
+        # fc_mu|fc_std: dW = dlat^T hT, db = column sums, dhT = dlat W
+        k.gemm(L.GEMM_TN, 1, 2 * H, H, B, self.dlat, 2 * H, 0, hT, H, 0, g["lat_w"], H, 0)
+        k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
+        k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
+        # encoder BPTT: gradient enters only through h_T
+        k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
+                  None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
+                  1, ENC_STEPS, B, self.ws_gru)
+        k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
+
+    # ------------------------------------------------------------------ update
+    def step(self, lr: float, lam: float):
+        """GD on every parameter (:498-499) + group-lasso prox on the heads' w_ih (:502-504)."""
+        k = self.k
+        if self.P > 0:
+            k.gd_prox_gc(self.theta["w_ih"], self.grad["w_ih"], self.mask_u8, self.col_norm, self.P, self.p,
+                         _f32(lr), _f32(lam * lr), lam > 0)
+        n_rest = self.theta.numel - self.rest_off
+        k.gd_step(self.theta.flat[self.rest_off:], self.grad.flat[self.rest_off:], n_rest, _f32(lr))
+
+    def prox_only(self, lam: float, lr: float):
+        if self.P > 0:
+            self.k.gd_prox_gc(self.theta["w_ih"], None, self.mask_u8, self.col_norm, self.P, self.p,
+                              0.0, _f32(lam * lr), True)
+
+    def column_norms(self) -> torch.Tensor:
+        """||w_ih[i][:, j]||_2 for the current weights -- what GC() stacks (:297-299)."""
+        if self.P > 0:
+            self.k.gd_prox_gc(self.theta["w_ih"], None, self.mask_u8, self.col_norm, self.P, self.p, 0.0, 0.0, False)
+        return self.col_norm
+
+    def ridge_value(self, lam_ridge: float) -> torch.Tensor:
+        """sum_i ridge_regularize(net_i, lam) (:321-325, :488) for this shard, as a device scalar."""
+        if lam_ridge == 0.0 or self.P == 0:
+            return torch.zeros((), dtype=torch.float32, device=self.device)
+        self.k.sumsq(self.theta["w_lin"], self.P * H, self.scratch[0:1])
+        self.k.sumsq(self.theta["w_hh"], self.P * G * H, self.scratch[1:2])
+        return lam_ridge * (self.scratch[0] + self.scratch[1])
+
+    # ------------------------------------------------------------------ snapshots (deepcopy / restore, :547/:558)
+    def snapshot(self) -> torch.Tensor:
+        return self.theta.flat.clone()
+
+    def restore(self, snap: torch.Tensor):
+        self.theta.flat.copy_(snap)
+
+    def zero_grad(self):
+        self.grad.flat.zero_()

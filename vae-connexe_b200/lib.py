@@ -1,0 +1,197 @@
+"""ctypes binding of libcrvae_b200.so (the C ABI declared in include/crvae_b200.h).
+
+The product path has no CPU fallback: if the shared library cannot be loaded, or the current
+device is not a B200-class (sm_100) GPU, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+_c_void_p, _c_int, _c_i64, _c_float, _c_double, _c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/crvae_b200.h declares
+SIGNATURES = {
+    "crvae_abi_version": (_c_int, []),
+    "crvae_last_error": (C.c_char_p, []),
+    "crvae_launch_count": (C.c_uint64, []),
+    "crvae_launch_count_reset": (None, []),
+    "crvae_check_device": (_c_int, []),
+    "crvae_gemm_f32": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_i64, _c_void_p, _c_int,
+                                _c_i64, _c_void_p, _c_int, _c_i64, _c_void_p, _c_i64, _c_int, _c_void_p]),
+    "crvae_proj_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p]),
+    "crvae_proj_wgrad_workspace": (_c_size_t, [_c_int] * 4),
+    "crvae_proj_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
+    "crvae_gru_fwd": (_c_int, [_c_void_p] * 5 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
+    "crvae_gru_bwd_workspace": (_c_size_t, [_c_int] * 2),
+    "crvae_gru_bwd": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 11 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
+    "crvae_latent_fwd": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_void_p]),
+    "crvae_latent_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_void_p,
+                                  _c_void_p, _c_int, _c_void_p]),
+    "crvae_mse_fwd_bwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p]),
+    "crvae_gd_step": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_float, _c_void_p]),
+    "crvae_gd_prox_gc": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_float, _c_float, _c_int, _c_void_p]),
+    "crvae_adam_step": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_double] * 4 + [_c_int, _c_void_p]),
+    "crvae_sumsq": (_c_int, [_c_void_p, _c_i64, _c_void_p, _c_void_p]),
+    "crvae_dot_small": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p]),
+    "crvae_axpy": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_float, _c_void_p]),
+    "crvae_debug_set_batch_tile": (None, [_c_int]),
+}
+
+GEMM_NT, GEMM_TN, GEMM_NN = 0, 1, 2
+KL_STANDARD, KL_SWAPPED = 0, 1
+
+_lib: Optional[C.CDLL] = None
+
+
+class CrvaeLibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree shared library (building it first when nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or os.environ.get("CRVAE_REBUILD"):
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.crvae_abi_version() != 1:
+        raise CrvaeLibraryError("libcrvae_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CrvaeLibraryError("libcrvae_b200 takes CUDA device pointers only (no CPU path exists)")
+    if t.data_ptr() % 4:
+        raise CrvaeLibraryError("misaligned tensor")
+    if t.dtype not in (torch.float32, torch.uint8):
+        raise CrvaeLibraryError(f"unsupported dtype {t.dtype}")
+    if not t.is_contiguous():
+        raise CrvaeLibraryError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Kernels:
+    """Thin checked wrappers: raise on any non-zero return code (no silent fallback)."""
+
+    device_type = "cuda"
+
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise CrvaeLibraryError("vae-connexe_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = load()
+        rc = self.lib.crvae_check_device()
+        if rc != 0:
+            raise CrvaeLibraryError(self.lib.crvae_last_error().decode())
+
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise CrvaeLibraryError(f"{what} failed (rc={rc}): {self.lib.crvae_last_error().decode()}")
+
+    def launch_count(self) -> int:
+        return int(self.lib.crvae_launch_count())
+
+    def reset_launch_count(self):
+        self.lib.crvae_launch_count_reset()
+
+    def set_batch_tile(self, rows: int):
+        self.lib.crvae_debug_set_batch_tile(int(rows))
+
+    def gemm(self, form, batch, M, N, K, A, lda, sA, Bm, ldb, sB, Cm, ldc, sC, bias=None, sBias=0, accumulate=False):
+        self._ck(self.lib.crvae_gemm_f32(form, batch, M, N, K, ptr(A), lda, sA, ptr(Bm), ldb, sB, ptr(Cm), ldc, sC,
+                                         ptr(bias), sBias, int(accumulate), stream_ptr()), "crvae_gemm_f32")
+
+    def proj_fwd(self, x, w_ih, b_ih, gates, P, T, B, K, t_skip):
+        self._ck(self.lib.crvae_proj_fwd(ptr(x), ptr(w_ih), ptr(b_ih), ptr(gates), P, T, B, K, t_skip, stream_ptr()),
+                 "crvae_proj_fwd")
+
+    def proj_wgrad_workspace(self, P, T, B, K) -> int:
+        return int(self.lib.crvae_proj_wgrad_workspace(P, T, B, K))
+
+    def proj_wgrad(self, dgates, x, mask, dw_ih, P, T, B, K, t_skip, ws):
+        self._ck(self.lib.crvae_proj_wgrad(ptr(dgates), ptr(x), ptr(mask), ptr(dw_ih), P, T, B, K, t_skip, ptr(ws),
+                                           stream_ptr()), "crvae_proj_wgrad")
+
+    def gru_fwd(self, gates, b_ih, w_hh, b_hh, h0, h0_stride, w_lin, b_lin, hs, ghn, pred, P, T, B, t_skip):
+        self._ck(self.lib.crvae_gru_fwd(ptr(gates), ptr(b_ih), ptr(w_hh), ptr(b_hh), ptr(h0), h0_stride, ptr(w_lin),
+                                        ptr(b_lin), ptr(hs), ptr(ghn), ptr(pred), P, T, B, t_skip, stream_ptr()),
+                 "crvae_gru_fwd")
+
+    def gru_bwd_workspace(self, P, B) -> int:
+        return int(self.lib.crvae_gru_bwd_workspace(P, B))
+
+    def gru_bwd(self, gates, ghn, hs, h0, h0_stride, w_hh, w_lin, dpred, dh_last, dhs, dw_hh, db_hh, db_ih, dw_lin,
+                db_lin, dh0, P, T, B, ws):
+        self._ck(self.lib.crvae_gru_bwd(ptr(gates), ptr(ghn), ptr(hs), ptr(h0), h0_stride, ptr(w_hh), ptr(w_lin),
+                                        ptr(dpred), ptr(dh_last), ptr(dhs), ptr(dw_hh), ptr(db_hh), ptr(db_ih), ptr(dw_lin),
+                                        ptr(db_lin), ptr(dh0), P, T, B, ptr(ws), stream_ptr()), "crvae_gru_bwd")
+
+    def latent_fwd(self, lat, eps, z, kl_out, B, kl_form):
+        self._ck(self.lib.crvae_latent_fwd(ptr(lat), ptr(eps), ptr(z), ptr(kl_out), B, kl_form, stream_ptr()),
+                 "crvae_latent_fwd")
+
+    def latent_bwd(self, dh0, P, dz_extra, lat, eps, beta, kl_form, dlat, dz_out, B):
+        self._ck(self.lib.crvae_latent_bwd(ptr(dh0), P, ptr(dz_extra), ptr(lat), ptr(eps), float(beta), kl_form,
+                                           ptr(dlat), ptr(dz_out), B, stream_ptr()), "crvae_latent_bwd")
+
+    def mse_fwd_bwd(self, pred, target, sse, dpred, err, P, T, B):
+        self._ck(self.lib.crvae_mse_fwd_bwd(ptr(pred), ptr(target), ptr(sse), ptr(dpred), ptr(err), P, T, B,
+                                            stream_ptr()), "crvae_mse_fwd_bwd")
+
+    def gd_step(self, theta, grad, n, lr):
+        self._ck(self.lib.crvae_gd_step(ptr(theta), ptr(grad), n, float(lr), stream_ptr()), "crvae_gd_step")
+
+    def gd_prox_gc(self, w_ih, dw_ih, mask, col_norm, P, K, lr, thr, do_prox):
+        self._ck(self.lib.crvae_gd_prox_gc(ptr(w_ih), ptr(dw_ih), ptr(mask), ptr(col_norm), P, K, float(lr),
+                                           float(thr), int(do_prox), stream_ptr()), "crvae_gd_prox_gc")
+
+    def adam_step(self, theta, grad, m, v, n, lr, b1, b2, eps, step):
+        self._ck(self.lib.crvae_adam_step(ptr(theta), ptr(grad), ptr(m), ptr(v), n, lr, b1, b2, eps, step,
+                                          stream_ptr()), "crvae_adam_step")
+
+    def sumsq(self, x, n, out):
+        self._ck(self.lib.crvae_sumsq(ptr(x), n, ptr(out), stream_ptr()), "crvae_sumsq")
+
+    def dot_small(self, x, n, scale, out):
+        self._ck(self.lib.crvae_dot_small(ptr(x), n, float(scale), ptr(out), stream_ptr()), "crvae_dot_small")
+
+    def axpy(self, y, x, n, alpha):
+        self._ck(self.lib.crvae_axpy(ptr(y), ptr(x), n, float(alpha), stream_ptr()), "crvae_axpy")
+
+
+_kernels: Optional[Kernels] = None
+
+
+def kernels() -> Kernels:
+    """The process-wide kernel table.  Always the CUDA library; tests/ may install a checker
+    backend with set_test_backend() to exercise the host logic on a machine without a GPU."""
+    global _kernels
+    if _kernels is None:
+        _kernels = Kernels()
+    return _kernels
+
+
+def set_test_backend(backend) -> None:
+    """TEST HOOK ONLY (tests/cpu_backend.py): replace the kernel table.  Nothing in the package
+    calls this; with no backend installed every entry point needs libcrvae_b200.so + a B200."""
+    global _kernels
+    _kernels = backend

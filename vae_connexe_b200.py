@@ -1,0 +1,12 @@
+"""Import shim: exposes the package that lives in the directory `vae-connexe_b200/` (hyphenated,
+hence not a Python identifier) under the importable name `vae_connexe_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vae-connexe_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)
