@@ -1,0 +1,230 @@
+"""P1 -- kernel-level parity: every C-ABI entry point on the B200 against the CPU oracle on the
+same seeded inputs (fp32, tolerance 1e-4 relative as BASELINE.json states; prox / GC decisions
+bit-exact).  Calls go through the C ABI (ctypes) exactly as the package does."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import crvae_oracle as O
+from tests.cpu_backend import OracleKernels
+
+pytestmark = pytest.mark.gpu
+H, G = 64, 192
+TOL = 1e-4
+
+
+def _k():
+    import vae_connexe_b200.lib as L
+    return L.Kernels()
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _rand(*s, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*s, generator=g) * scale
+
+
+@pytest.mark.parametrize("form,M,N,K", [(0, 256, 128, 64), (0, 300, 192, 100), (0, 2304, 192, 10), (1, 128, 64, 256),
+                                        (1, 192, 100, 2304), (1, 1, 128, 256), (2, 256, 64, 128), (2, 77, 33, 19)])
+def test_gemm_forms(form, M, N, K):
+    k, o = _k(), OracleKernels()
+    if form == 0: A, B = _rand(M, K, seed=1), _rand(N, K, seed=2)
+    elif form == 1: A, B = _rand(K, M, seed=1), _rand(K, N, seed=2)
+    else: A, B = _rand(M, K, seed=1), _rand(K, N, seed=2)
+    bias = _rand(N, seed=3)
+    C_ref = torch.zeros(M, N)
+    o.gemm(form, 1, M, N, K, A, A.shape[1], 0, B, B.shape[1], 0, C_ref, N, 0, bias, 0)
+    C = torch.zeros(M, N, device="cuda")
+    k.gemm(form, 1, M, N, K, A.cuda(), A.shape[1], 0, B.cuda(), B.shape[1], 0, C, N, 0, bias.cuda(), 0)
+    assert _rel(C, C_ref) < 1e-5
+    k.gemm(form, 1, M, N, K, A.cuda(), A.shape[1], 0, B.cuda(), B.shape[1], 0, C, N, 0, None, 0, accumulate=True)
+    assert _rel(C, 2 * C_ref - bias) < 1e-5
+
+
+@pytest.mark.parametrize("P,T,B,K,t_skip", [(3, 10, 64, 10, 1), (5, 10, 256, 100, 1), (1, 10, 256, 100, 0), (2, 4, 40, 7, 1)])
+def test_projection_fwd_and_wgrad(P, T, B, K, t_skip):
+    k, o = _k(), OracleKernels()
+    x, w, b = _rand(T, B, K, seed=1), _rand(P, G, K, seed=2, scale=0.1), _rand(P, G, seed=3)
+    mask = (torch.rand(P, K, generator=torch.Generator().manual_seed(4)) < 0.6).to(torch.uint8)
+    g_ref = torch.full((P, T, B, G), 7.0)
+    o.proj_fwd(x, w, b, g_ref, P, T, B, K, t_skip)
+    g_gpu = torch.full((P, T, B, G), 7.0, device="cuda")
+    k.proj_fwd(x.cuda(), w.cuda(), b.cuda(), g_gpu, P, T, B, K, t_skip)
+    assert _rel(g_gpu, g_ref) < 1e-5
+    assert torch.equal(g_gpu[:, :t_skip].cpu(), g_ref[:, :t_skip])          # skipped steps untouched
+    dg = _rand(P, T, B, G, seed=5)
+    for m in (None, mask):
+        dw_ref = torch.zeros(P, G, K)
+        o.proj_wgrad(dg, x, m, dw_ref, P, T, B, K, t_skip, None)
+        ws = torch.zeros(k.proj_wgrad_workspace(P, T, B, K) // 4 + 4, device="cuda")
+        dw = torch.zeros(P, G, K, device="cuda")
+        k.proj_wgrad(dg.cuda(), x.cuda(), None if m is None else m.cuda(), dw, P, T, B, K, t_skip, ws)
+        assert _rel(dw, dw_ref) < 1e-5
+        if m is not None:
+            assert torch.equal(dw.cpu()[(m == 0)[:, None, :].expand(P, G, K)], torch.zeros(int((m == 0).sum()) * G))
+
+
+@pytest.mark.parametrize("P,T,B,tile,lin,t_skip,shared_h0", [
+    (3, 10, 64, 16, True, 1, True), (3, 10, 64, 32, True, 1, True), (3, 10, 64, 64, True, 1, True),
+    (2, 10, 100, 64, True, 1, False), (1, 10, 256, 0, False, 0, True), (7, 3, 37, 32, True, 0, False),
+    (40, 10, 256, 0, True, 1, True)])
+def test_gru_forward_backward(P, T, B, tile, lin, t_skip, shared_h0):
+    k, o = _k(), OracleKernels()
+    k.set_batch_tile(tile)
+    try:
+        gi = _rand(P, T, B, G, seed=1)
+        b_ih, w_hh, b_hh = _rand(P, G, seed=2, scale=0.2), _rand(P, G, H, seed=3, scale=0.125), _rand(P, G, seed=4, scale=0.2)
+        h0 = _rand(B, H, seed=5) if shared_h0 else _rand(P, B, H, seed=5)
+        stride = 0 if shared_h0 else B * H
+        w_lin, b_lin = (_rand(P, H, seed=6, scale=0.2), _rand(P, seed=7)) if lin else (None, None)
+        c = lambda t: None if t is None else t.cuda()
+        out_ref = dict(g=gi.clone(), hs=torch.zeros(P, T, B, H), ghn=torch.zeros(P, T, B, H), pred=torch.zeros(P, T, B) if lin else None)
+        o.gru_fwd(out_ref["g"], b_ih, w_hh, b_hh, h0, stride, w_lin, b_lin, out_ref["hs"], out_ref["ghn"], out_ref["pred"], P, T, B, t_skip)
+        out = dict(g=gi.clone().cuda(), hs=torch.zeros(P, T, B, H, device="cuda"), ghn=torch.zeros(P, T, B, H, device="cuda"),
+                   pred=torch.zeros(P, T, B, device="cuda") if lin else None)
+        k.gru_fwd(out["g"], c(b_ih), c(w_hh), c(b_hh), c(h0), stride, c(w_lin), c(b_lin), out["hs"], out["ghn"], out["pred"], P, T, B, t_skip)
+        torch.cuda.synchronize()
+        for name in ("g", "hs", "ghn") + (("pred",) if lin else ()):
+            assert _rel(out[name], out_ref[name]) < 2e-5, name
+        # backward, fed with the ORACLE's forward state so the comparison isolates the backward kernel
+        dpred = _rand(P, T, B, seed=8) if lin else None
+        dh_last = _rand(P, B, H, seed=9, scale=0.1)
+        dhs = _rand(P, T, B, H, seed=10, scale=0.1)
+        z = lambda *s: torch.zeros(*s)
+        ref = dict(g=out_ref["g"].clone(), dw_hh=z(P, G, H), db_hh=z(P, G), db_ih=z(P, G), dw_lin=z(P, H) if lin else None,
+                   db_lin=z(P) if lin else None, dh0=z(P, B, H))
+        o.gru_bwd(ref["g"], out_ref["ghn"], out_ref["hs"], h0, stride, w_hh, w_lin, dpred, dh_last, dhs, ref["dw_hh"], ref["db_hh"],
+                  ref["db_ih"], ref["dw_lin"], ref["db_lin"], ref["dh0"], P, T, B, None)
+        gpu = {n: (None if v is None else torch.zeros_like(v).cuda()) for n, v in ref.items()}
+        gpu["g"] = out_ref["g"].clone().cuda()
+        ws = torch.zeros(k.gru_bwd_workspace(P, B) // 4 + 4, device="cuda")
+        k.gru_bwd(gpu["g"], c(out_ref["ghn"]), c(out_ref["hs"]), c(h0), stride, c(w_hh), c(w_lin), c(dpred), c(dh_last), c(dhs),
+                  gpu["dw_hh"], gpu["db_hh"], gpu["db_ih"], gpu["dw_lin"], gpu["db_lin"], gpu["dh0"], P, T, B, ws)
+        torch.cuda.synchronize()
+        for name, v in ref.items():
+            if v is not None:
+                assert _rel(gpu[name], v) < 5e-5, name
+    finally:
+        k.set_batch_tile(0)
+
+
+@pytest.mark.parametrize("form", [0, 1])
+@pytest.mark.parametrize("B", [64, 256])
+def test_latent_fwd_bwd(form, B):
+    k, o = _k(), OracleKernels()
+    lat, eps = _rand(B, 2 * H, seed=1, scale=0.5), _rand(B, H, seed=2)
+    z_ref, kl_ref = torch.zeros(B, H), torch.zeros(1)
+    o.latent_fwd(lat, eps, z_ref, kl_ref, B, form)
+    z, kl = torch.zeros(B, H, device="cuda"), torch.zeros(1, device="cuda")
+    k.latent_fwd(lat.cuda(), eps.cuda(), z, kl, B, form)
+    assert _rel(z, z_ref) < 1e-6 and _rel(kl, kl_ref) < 1e-6
+    P = 9
+    dh0, extra = _rand(P, B, H, seed=3), _rand(B, H, seed=4)
+    for ex in (None, extra):
+        d_ref, dz_ref = torch.zeros(B, 2 * H), torch.zeros(B, H)
+        o.latent_bwd(dh0, P, ex, lat, eps, 0.1, form, d_ref, dz_ref, B)
+        d, dz = torch.zeros(B, 2 * H, device="cuda"), torch.zeros(B, H, device="cuda")
+        k.latent_bwd(dh0.cuda(), P, None if ex is None else ex.cuda(), lat.cuda(), eps.cuda(), 0.1, form, d, dz, B)
+        assert _rel(d, d_ref) < 1e-5 and _rel(dz, dz_ref) < 1e-6
+    # two-stage form used across ranks: head sum only, then pointwise on the reduced dz
+    dz = torch.zeros(B, H, device="cuda")
+    k.latent_bwd(dh0.cuda(), P, None, None, None, 0.0, form, None, dz, B)
+    d2 = torch.zeros(B, 2 * H, device="cuda")
+    k.latent_bwd(None, 0, dz, lat.cuda(), eps.cuda(), 0.1, form, d2, None, B)
+    d_ref = torch.zeros(B, 2 * H)
+    o.latent_bwd(dh0, P, None, lat, eps, 0.1, form, d_ref, None, B)
+    assert _rel(d2, d_ref) < 1e-5
+
+
+def test_mse_fwd_bwd():
+    k, o = _k(), OracleKernels()
+    P, T, B = 11, 10, 256
+    pred, tgt = _rand(P, T, B, seed=1), _rand(P, T, B, seed=2)
+    r = dict(sse=torch.zeros(P), dp=torch.zeros(P, T, B), err=torch.zeros(P, T, B))
+    o.mse_fwd_bwd(pred, tgt, r["sse"], r["dp"], r["err"], P, T, B)
+    g = {n: torch.zeros_like(v).cuda() for n, v in r.items()}
+    k.mse_fwd_bwd(pred.cuda(), tgt.cuda(), g["sse"], g["dp"], g["err"], P, T, B)
+    assert _rel(g["sse"], r["sse"]) < 1e-6
+    assert torch.equal(g["err"].cpu(), r["err"])
+    assert _rel(g["dp"], r["dp"]) < 1e-6
+    out = torch.zeros(1, device="cuda")
+    k.dot_small(g["sse"], P, 1.0 / (T * B), out)
+    assert abs(float(out) - float(r["sse"].sum() / (T * B))) < 1e-5
+
+
+@pytest.mark.parametrize("P,K", [(4, 10), (100, 100), (3, 33)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_gd_prox_gc_bit_exact(P, K, masked):
+    """GD + prox on identical tensors: same zero pattern as torch's prox_update (:308-314) and
+    weights equal to 1 ulp-level (the column norm is the only non-bit-identical intermediate)."""
+    k = _k()
+    lam, lr = 0.1, 5e-2
+    thr = np.float32(lam * lr)
+    gen = torch.Generator().manual_seed(P * 1000 + K)
+    w = torch.randn(P, G, K, generator=gen) * 0.05
+    # adversarial columns: norms at thr*(1 +- eps), exactly zero, far above/below
+    unit = w / torch.norm(w, dim=1, keepdim=True)
+    scales = torch.tensor([1 + 1e-3, 1 - 1e-3, 1 + 1e-5, 1 - 1e-5, 0.0, 0.3, 3.0, 1 + 1e-6, 1 - 1e-6])[: min(K, 9)]
+    w[:, :, : len(scales)] = unit[:, :, : len(scales)] * scales * float(thr)
+    dw = torch.zeros(P, G, K)
+    dw[:, :, len(scales):] = torch.randn(P, G, K - len(scales), generator=gen) * 0.01
+    mask = (torch.rand(P, K, generator=gen) < 0.7).to(torch.uint8) if masked else None
+    if masked:
+        w = w * mask[:, None, :].float()
+    w_ref = w - np.float32(lr) * dw
+    if masked:
+        w_ref = w_ref * mask[:, None, :].float()
+    w_ref = O.prox_update(w_ref, lam, lr)
+    wg, cn = w.clone().cuda(), torch.zeros(P, K, device="cuda")
+    k.gd_prox_gc(wg, dw.cuda(), None if mask is None else mask.cuda(), cn, P, K, float(np.float32(lr)), float(thr), True)
+    nz_ref = torch.norm(w_ref, dim=1) > 0
+    assert torch.equal((cn > 0).cpu(), nz_ref)                                  # GC decision bit-exact
+    assert torch.equal((wg != 0).any(1).cpu(), nz_ref)
+    assert _rel(wg, w_ref) < 1e-5
+    assert _rel(cn, torch.norm(w_ref, dim=1)) < 1e-5
+    # norms-only and prox-only entry forms
+    cn2 = torch.zeros(P, K, device="cuda")
+    before = wg.clone()
+    k.gd_prox_gc(wg, None, None if mask is None else mask.cuda(), cn2, P, K, 0.0, 0.0, False)
+    assert torch.equal(wg, before) and torch.equal(cn2, cn)
+
+
+def test_gd_step_bit_exact():
+    k = _k()
+    th, g = _rand(100003, seed=1), _rand(100003, seed=2)
+    ref = th.clone()
+    ref -= np.float32(0.05) * g
+    t = th.clone().cuda()
+    k.gd_step(t, g.cuda(), th.numel(), float(np.float32(0.05)))
+    assert torch.equal(t.cpu(), ref)
+
+
+def test_adam_matches_torch():
+    k = _k()
+    n = 50001
+    p0 = _rand(n, seed=1)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    th, m, v = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 8):
+        g = _rand(n, seed=10 + step)
+        ref.grad = g.clone()
+        opt.step()
+        k.adam_step(th, g.cuda(), m, v, n, 1e-3, 0.9, 0.999, 1e-8, step)
+        assert float((th.cpu() - ref.detach()).abs().max()) < 2e-7
+
+
+def test_sumsq_axpy():
+    k = _k()
+    x = _rand(192 * 64 * 7, seed=1)
+    out = torch.zeros(1, device="cuda")
+    k.sumsq(x.cuda(), x.numel(), out)
+    assert abs(float(out) - float((x.double() ** 2).sum())) < 1e-6 * float((x.double() ** 2).sum())
+    y = _rand(1000, seed=2)
+    yg = y.clone().cuda()
+    k.axpy(yg, x[:1000].cuda(), 1000, 0.5)
+    assert _rel(yg, y + 0.5 * x[:1000]) < 1e-6

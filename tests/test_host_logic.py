@@ -1,0 +1,172 @@
+"""Host-side logic of the package (module mirrors, trainers, RNG order, snapshots) exercised on CPU
+through the oracle-backed checker backend (tests/cpu_backend.py) and compared with the golden
+vectors produced by the reference.  No CUDA kernel runs here; kernel parity is tests/test_gpu_*.py."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crvae_oracle as O
+from tests.conftest import GOLDEN
+
+H = 64
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def step():
+    return np.load(os.path.join(GOLDEN, "p4_step.npz"))
+
+
+@pytest.fixture(scope="module")
+def traj():
+    return np.load(os.path.join(GOLDEN, "p10_traj.npz"))
+
+
+def test_module_surface_matches_reference(cpu_backend, step):
+    import vae_connexe_b200 as V
+    p = 4
+    torch.manual_seed(0)
+    m = V.CRVAE(p, np.ones((p, p)), 64)
+    assert (m.p, m.hidden) == (p, 64) and m.connection.shape == (p, p) and len(m.networks) == p
+    sd = m.state_dict()
+    expect = ["gru_left.weight_ih_l0", "gru_left.weight_hh_l0", "gru_left.bias_ih_l0", "gru_left.bias_hh_l0",
+              "fc_mu.weight", "fc_mu.bias", "fc_std.weight", "fc_std.bias"]
+    for i in range(p):
+        expect += [f"networks.{i}.gru.weight_ih_l0", f"networks.{i}.gru.weight_hh_l0", f"networks.{i}.gru.bias_ih_l0",
+                   f"networks.{i}.gru.bias_hh_l0", f"networks.{i}.linear.weight", f"networks.{i}.linear.bias"]
+    assert list(sd.keys()) == expect
+    assert [n for n, _ in m.named_parameters()] == expect            # same parameter order as the reference (:498)
+    assert sd["networks.1.linear.weight"].shape == (1, 64) and sd["networks.1.gru.weight_ih_l0"].shape == (192, p)
+    prm = O.params_from_state_dict(sd, np.ones((p, p)))
+    for k in O.PARAM_KEYS:
+        assert np.array_equal(prm[k].numpy(), step["init." + k]), k   # torch.manual_seed parity with the reference
+    # parameters are views of the fused arena: an in-place update through .data is seen by the engine
+    w = m.networks[2].gru.weight_hh_l0
+    w.data -= 1.0
+    assert torch.equal(m.engine.theta["w_hh"][2], w.data)
+    # load_state_dict round trip
+    m2 = V.CRVAE(p, np.ones((p, p)), 64)
+    m2.load_state_dict(sd)
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_deepcopy_restore_and_rng_untouched(cpu_backend):
+    import vae_connexe_b200 as V
+    torch.manual_seed(3)
+    m = V.CRVAE(5, np.ones((5, 5)), 64)
+    st = torch.get_rng_state()
+    best = copy.deepcopy(m)                                           # the reference's snapshot (:547)
+    assert torch.equal(torch.get_rng_state(), st)
+    assert torch.equal(best.engine.theta.flat, m.engine.theta.flat)
+    m.engine.theta.flat.add_(1.0)
+    assert not torch.equal(best.engine.theta.flat, m.engine.theta.flat)
+    V.restore_parameters(m, best)                                     # (:327-330, :558)
+    assert torch.equal(best.engine.theta.flat, m.engine.theta.flat)
+    assert m.networks[0].gru.weight_ih_l0.data_ptr() == m.engine.theta["w_ih"][0].data_ptr()   # still a view
+
+
+def test_functional_helpers_match_oracle(cpu_backend):
+    import vae_connexe_b200 as V
+    torch.manual_seed(4)
+    p = 6
+    m = V.CRVAE(p, np.ones((p, p)), 64)
+    w0 = m.engine.theta["w_ih"].clone()
+    lam, lr = 0.5, 0.1
+    reg = float(V.regularize(m.networks[1], lam))
+    assert abs(reg - float(lam * torch.norm(w0[1], dim=0).sum())) < 1e-5
+    rid = float(V.ridge_regularize(m.networks[1], 0.3))
+    exp = 0.3 * (float((m.engine.theta["w_lin"][1] ** 2).sum()) + float((m.engine.theta["w_hh"][1] ** 2).sum()))
+    assert abs(rid - exp) < 1e-5 * exp
+    V.prox_update(m.networks[1], lam, lr)
+    assert _rel(m.engine.theta["w_ih"][1], O.prox_update(w0[1:2], lam, lr)[0]) < 1e-6
+    assert torch.equal(m.engine.theta["w_ih"][0], w0[0])              # only that head was touched
+    data = torch.arange(60, dtype=torch.float32).reshape(30, 2)
+    a, b = V.arrange_input(data, 20)
+    a2, b2 = O.arrange_input(data, 20)
+    assert torch.equal(a, a2) and torch.equal(b, b2) and a.shape == (10, 20, 2)
+
+
+def test_reference_style_autograd_loop(cpu_backend, step):
+    """The reference's own loop statements (:482-506) run against the mirror classes."""
+    import vae_connexe_b200 as V
+    p = 4
+    torch.manual_seed(0); np.random.seed(0)
+    crvae = V.CRVAE(p, np.ones((p, p)), 64)
+    X = torch.from_numpy(step["X"])
+    lam_ridge, beta, lr, lam = float(step["lam_ridge"]), float(step["beta"]), float(step["lr"]), float(step["lam"])
+    loss_fn = torch.nn.MSELoss()
+    pred, mu, log_var = crvae(X)
+    loss = sum([loss_fn(pred[i][:, :, 0], X[:, 10:, i]) for i in range(p)])
+    mmd = (-0.5 * (1 + log_var - mu ** 2 - torch.exp(log_var)).sum(dim=-1).sum(dim=0)).mean(dim=0)
+    smooth = loss + beta * mmd
+    assert abs(float(loss) - float(step["loss"])) < 1e-5 and abs(float(mmd) - float(step["kl"])) < 1e-5
+    _ = crvae(X)                      # a later forward (like the check block's :522) must not corrupt the backward
+    smooth.backward()
+    g = crvae.engine.grad
+    assert _rel(g["w_ih"], step["grad.w_ih"]) < 1e-5 and _rel(g["enc_w_ih"], step["grad.enc_w_ih"]) < 1e-5
+    assert _rel(g["b_hh"], step["grad.b_hh"]) < 1e-5
+    assert _rel(crvae.networks[3].gru.weight_ih_l0.grad, step["grad.w_ih"][3]) < 1e-5
+    for param in crvae.parameters():
+        param.data -= lr * param.grad
+    for net in crvae.networks:
+        V.prox_update(net, lam, lr)
+    crvae.zero_grad()
+    assert float(crvae.engine.grad.flat.abs().sum()) == 0.0
+    assert np.array_equal(crvae.GC().numpy(), step["GC"])
+
+
+def test_train_phase1_tracks_reference_log(cpu_backend, traj):
+    """Host logic of train_phase1 (batch draw, noise-draw order, check block, best-model restore)
+    against the reference's golden log, first 101 iterations; generator state ends where the
+    reference's does (planned draw count)."""
+    import vae_connexe_b200 as V
+    Xt = torch.from_numpy(traj["data"].T.copy())[None]
+    torch.manual_seed(0); np.random.seed(0)
+    m = V.CRVAE(10, np.ones((10, 10)), 64)
+    log = []
+    out = V.train_phase1(m, Xt, context=20, lam=0.1, lam_ridge=0, lr=5e-2, max_iter=101, check_every=50, verbose=0, log=log)
+    assert out == [] and m.best_it == 100
+    for i, r in enumerate(log):
+        assert r["it"] == int(traj["log_it"][i])
+        assert abs(r["mean_loss"] - traj["log_loss"][i]) < 2e-6 and abs(r["kl"] - traj["log_kl"][i]) < 2e-6
+        assert r["usage"] == traj["log_usage"][i]
+    # 1 + 101 + 2*3 draws of (256,64) were consumed: same generator position as an explicit replay
+    nxt = torch.randn(4)
+    torch.manual_seed(0)
+    torch.nn.GRU(10, 64); torch.nn.Linear(64, 64); torch.nn.Linear(64, 64)
+    for _ in range(10):
+        torch.nn.GRU(10, 64); torch.nn.Linear(64, 1)
+    torch.randn(108, 256, 64)
+    assert torch.equal(nxt, torch.randn(4))
+
+
+def test_ragged_init_matches_reference_order(cpu_backend):
+    """Pruned connection: heads are built from COLUMN i of the matrix (the reference's quirk, :201,
+    :115) and draw their init in declaration order."""
+    import vae_connexe_b200 as V
+    p = 5
+    conn = np.array([[1, 1, 0, 0, 1], [0, 1, 1, 0, 0], [0, 0, 1, 1, 0], [1, 0, 0, 1, 1], [0, 0, 0, 0, 1]])
+    torch.manual_seed(11)
+    m = V.CRVAE(p, conn, 64)
+    torch.manual_seed(11)
+    torch.nn.GRU(p, 64, batch_first=True); torch.nn.Linear(64, 64); torch.nn.Linear(64, 64)
+    sd = m.state_dict()
+    for i in range(p):
+        k_i = int(conn[:, i].sum())
+        gru = torch.nn.GRU(k_i, 64, batch_first=True); lin = torch.nn.Linear(64, 1)
+        assert torch.equal(sd[f"networks.{i}.gru.weight_ih_l0"], gru.weight_ih_l0.detach())
+        assert torch.equal(sd[f"networks.{i}.linear.weight"], lin.weight.detach())
+        cols = np.where(conn[:, i] != 0)[0]
+        dense = m.engine.theta["w_ih"][i]
+        assert torch.equal(dense[:, cols], gru.weight_ih_l0.detach())
+        rest = np.setdiff1d(np.arange(p), cols)
+        assert float(dense[:, rest].abs().sum()) == 0.0
+    assert m.networks[0].p == int(conn[:, 0].sum())

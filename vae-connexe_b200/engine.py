@@ -97,12 +97,17 @@ class CRVAEEngine:
         assert X.dim() == 3 and X.shape[2] == self.p and X.shape[1] == ENC_STEPS + DEC_STEPS
         X = X.to(self.device, torch.float32)
         B = X.shape[0]
-        self.enc_in = X[:, :ENC_STEPS].transpose(0, 1).contiguous()                       # [Te,B,p]
-        self.dec_in = torch.cat([torch.zeros_like(X[:, :1]), X[:, ENC_STEPS:-1]], 1).transpose(0, 1).contiguous()
         lo, hi = self.head_off, self.head_off + self.P
-        self.target = X[:, ENC_STEPS:, lo:hi].permute(2, 1, 0).contiguous()               # [P,Td,B]
         if self.B != B:
             self._alloc(B)
+            self.enc_in = torch.empty(ENC_STEPS, B, self.p, dtype=torch.float32, device=self.device)
+            self.dec_in = torch.zeros(DEC_STEPS, B, self.p, dtype=torch.float32, device=self.device)
+            self.target = torch.empty(max(self.P, 1), DEC_STEPS, B, dtype=torch.float32, device=self.device)
+        # in-place (re)binding keeps the buffer addresses stable for captured CUDA graphs
+        self.enc_in.copy_(X[:, :ENC_STEPS].transpose(0, 1))                               # [Te,B,p]
+        self.dec_in[1:].copy_(X[:, ENC_STEPS:-1].transpose(0, 1))                         # [Td,B,p], step 0 stays 0
+        if self.P > 0:
+            self.target[: self.P].copy_(X[:, ENC_STEPS:, lo:hi].permute(2, 1, 0))         # [P,Td,B]
 
     def _alloc(self, B: int):
         P, dev = self.P, self.device
