@@ -81,6 +81,15 @@ int crvae_gemm_f32(int form, int batch, int M, int N, int K,
 int crvae_proj_fwd(const float* x, const float* w_ih, const float* b_ih, float* gates,
                    int P, int T, int B, int K, int t_skip, void* stream);
 
+/* Tensor-core form of crvae_proj_fwd: tcgen05.mma kind::tf32 fed by TMA, accumulators in TMEM,
+ * error-compensated 3xTF32 (A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi, fp32 accumulate) so the result agrees
+ * with the fp32 reference to ~1e-6 relative.  Operands arrive pre-split (crvae_split_tf32):
+ * x_hi/x_lo [T,B,K], w_hi/w_lo [P,G,K].  Needs K % 4 == 0 (TMA row pitch).                    */
+int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                      const float* b_ih, float* gates, int P, int T, int B, int K, int t_skip, void* stream);
+/* hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i] (exact in fp32)               */
+int crvae_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);
+
 /* Weight gradient of the projection (autograd of the above, :497):
  *   dw_ih[i] (G x K) = sum_{t>=t_skip,b} dgates[i][t][b][:]^T x[t][b][:]   (x mask[i][k] if mask)
  * workspace: >= crvae_proj_wgrad_workspace(P,T,B,K) bytes (split-reduction partials).          */

@@ -68,6 +68,28 @@ def test_projection_fwd_and_wgrad(P, T, B, K, t_skip):
             assert torch.equal(dw.cpu()[(m == 0)[:, None, :].expand(P, G, K)], torch.zeros(int((m == 0).sum()) * G))
 
 
+@pytest.mark.parametrize("P,T,B,K,t_skip", [(1, 10, 256, 100, 0), (3, 10, 64, 12, 1), (5, 10, 256, 100, 1), (2, 4, 40, 36, 1),
+                                            (100, 10, 256, 100, 1), (2, 10, 256, 1000, 1)])
+def test_projection_tensor_core_3xtf32(P, T, B, K, t_skip):
+    """tcgen05 + TMA projection (3xTF32) against the fp64 result: fp32-grade accuracy required."""
+    k = _k()
+    x, w, b = _rand(T, B, K, seed=1), _rand(P, G, K, seed=2, scale=0.1), _rand(P, G, seed=3)
+    ref = (torch.einsum("tbk,pgk->ptbg", x.double(), w.double()) + b.double()[:, None, None, :])
+    xc, wc = x.cuda(), w.cuda()
+    xh, xl, wh, wl = (torch.empty_like(t) for t in (xc, xc, wc, wc))
+    k.split_tf32(xc, xh, xl, xc.numel()); k.split_tf32(wc, wh, wl, wc.numel())
+    assert torch.equal(xh + xl, xc) and float((xh.view(torch.int32) & 0x1FFF).abs().sum()) == 0     # exact split, hi is tf32
+    g = torch.full((P, T, B, G), 7.0, device="cuda")
+    k.proj_fwd_tc(xh, xl, wh, wl, b.cuda(), g, P, T, B, K, t_skip)
+    torch.cuda.synchronize()
+    err_tc = _rel(g[:, t_skip:], ref[:, t_skip:])
+    g32 = torch.full((P, T, B, G), 7.0, device="cuda")
+    k.proj_fwd(xc, wc, b.cuda(), g32, P, T, B, K, t_skip)
+    err_f32 = _rel(g32[:, t_skip:], ref[:, t_skip:])
+    assert err_tc < (2e-6 if K <= 128 else 2e-5), (err_tc, err_f32)      # TMEM accumulation rounds differently from FFMA
+    assert torch.equal(g[:, :t_skip].cpu(), torch.full((P, t_skip, B, G), 7.0))
+
+
 @pytest.mark.parametrize("P,T,B,tile,lin,t_skip,shared_h0", [
     (3, 10, 64, 16, True, 1, True), (3, 10, 64, 32, True, 1, True), (3, 10, 64, 64, True, 1, True),
     (2, 10, 100, 64, True, 1, False), (1, 10, 256, 0, False, 0, True), (7, 3, 37, 32, True, 0, False),

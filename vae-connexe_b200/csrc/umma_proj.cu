@@ -1,0 +1,225 @@
+// Multi-head input projection on the 5th-generation tensor cores (tcgen05), fed by TMA.
+//
+//   gates[i][t][b][:] = b_ih[i] + x[t][b][:] . w_ih[i]^T        (GRU.forward, CRVAE_lorenz96.py:115-119)
+//
+// tcgen05 has no fp32 MMA (kind::tf32 / f16 / f8 only), and the path must agree with the fp32
+// reference to 1e-4, so the contraction is error-compensated "3xTF32": every operand is pre-split
+// into hi = tf32(v) and lo = v - hi (exact in fp32) and  A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi
+// is accumulated in fp32 in TMEM (the dropped Alo.Blo term is ~2^-22 relative).
+//
+// One CTA computes one [128 rows x 192 gate columns] tile = 128 (t,b) rows of one head:
+//   warp 0   : TMA producer  (4 boxes per 32-wide K chunk: A_hi, A_lo [128x32], B_hi, B_lo [192x32], SWIZZLE_128B)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per 8-wide K step)
+//   warps 2-5: epilogue, tcgen05.ld of the accumulator (lane = row) + bias -> global
+// smem ring: 2 stages x 80 KB, full/empty mbarriers; accumulator 128 lanes x 192 fp32 columns of TMEM.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace crvae {
+
+constexpr int TC_BM = 128;          // rows per tile (UMMA M)
+constexpr int TC_BN = CRVAE_G;      // 192 gate columns (UMMA N)
+constexpr int TC_BK = 32;           // K elements per stage chunk (128-byte rows)
+constexpr int TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;    // 16384
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;    // 24576
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 81920
+constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct ProjTcArgs {
+    float* C;               // gates + t_skip*B*G
+    const float* bias;      // [P][G]
+    long long c_head_stride;
+    int M, K;
+};
+
+__global__ void __launch_bounds__(192, 1)
+proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, ProjTcArgs a) {
+    using namespace umma;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* tmem_full = empty + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, head = blockIdx.y;
+    const int nchunks = (a.K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            mbar_init(tmem_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<TC_TMEM_COLS>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * TC_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
+                tma_load_2d(st, &tmA_hi, &full[s], c * TC_BK, m_tile * TC_BM);
+                tma_load_2d(st + TC_A_BYTES, &tmA_lo, &full[s], c * TC_BK, m_tile * TC_BM);
+                tma_load_2d(st + 2 * TC_A_BYTES, &tmB_hi, &full[s], c * TC_BK, head * TC_BN);
+                tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full[s], c * TC_BK, head * TC_BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(TC_BM, TC_BN, false, false);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * TC_STAGE_BYTES);
+                const uint64_t a_hi = smem_desc_k_sw128(st), a_lo = smem_desc_k_sw128(st + TC_A_BYTES);
+                const uint64_t b_hi = smem_desc_k_sw128(st + 2 * TC_A_BYTES), b_lo = smem_desc_k_sw128(st + 2 * TC_A_BYTES + TC_B_BYTES);
+                int ksteps = (a.K - c * TC_BK + 7) / 8;
+                if (ksteps > TC_BK / 8) ksteps = TC_BK / 8;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t adv = static_cast<uint64_t>(2 * k);        // 8 tf32 = 32 B = 2 x 16 B
+                    mma_tf32_ss(tmem_base, a_lo + adv, b_hi + adv, idesc, (c | k) != 0);
+                    mma_tf32_ss(tmem_base, a_hi + adv, b_lo + adv, idesc, true);
+                    mma_tf32_ss(tmem_base, a_hi + adv, b_hi + adv, idesc, true);
+                }
+                mma_commit(&empty[s]);          // smem stage is free once these MMAs have read it
+            }
+            mma_commit(tmem_full);              // accumulator complete
+        }
+    } else {
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int row = m_tile * TC_BM + q * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        float* crow = a.C + static_cast<long long>(head) * a.c_head_stride + static_cast<long long>(row) * TC_BN;
+        const float* bias = a.bias + static_cast<long long>(head) * TC_BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), v);
+            tmem_ld_wait();
+            if (row < a.M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                    *reinterpret_cast<float4*>(crow + c0 + j) =
+                        make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+    }
+}
+
+// hi = tf32(v) (round to nearest, ties away), lo = v - hi (exact)
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        float v = src[e];
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        float hf = __uint_as_float(h);
+        hi[e] = hf;
+        lo[e] = __fsub_rn(v, hf);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled entry point unavailable");
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp32 matrix [rows][inner] (inner contiguous, row stride = row_stride_elems), box {32 x box_rows}, 128B swizzle
+int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+                 uint32_t box_inner, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return CRVAE_E_BADARG;
+    cuuint64_t gdim[2] = {inner, rows};
+    cuuint64_t gstr[1] = {row_stride_elems * sizeof(float)};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu stride=%llu", (int)r, (unsigned long long)inner,
+                  (unsigned long long)rows, (unsigned long long)row_stride_elems);
+        return CRVAE_E_BADARG;
+    }
+    return 0;
+}
+
+}  // namespace crvae
+
+using namespace crvae;
+
+extern "C" int crvae_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream) {
+    CRVAE_REQUIRE(src && hi && lo && n >= 0, "bad argument");
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    split_tf32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, hi, lo, n);
+    return check_launch("split_tf32_kernel");
+}
+
+extern "C" int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                                 const float* b_ih, float* gates, int P, int T, int B, int K, int t_skip, void* stream) {
+    CRVAE_REQUIRE(x_hi && x_lo && w_hi && w_lo && b_ih && gates, "null operand");
+    CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0 && K > 0 && t_skip >= 0 && t_skip <= T, "bad size");
+    CRVAE_REQUIRE(K % 4 == 0, "tensor-core projection needs K % 4 == 0 (16-byte TMA row pitch); use crvae_proj_fwd");
+    CRVAE_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo) && aligned16(gates) && aligned16(b_ih),
+                  "16-byte alignment");
+    const int M = (T - t_skip) * B;
+    if (P == 0 || M == 0) return 0;
+    const long long xoff = (long long)t_skip * B * K;
+    CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+    int rc;
+    if ((rc = make_tmap_2d(&tA_hi, x_hi + xoff, K, M, K, TC_BK, TC_BM))) return rc;
+    if ((rc = make_tmap_2d(&tA_lo, x_lo + xoff, K, M, K, TC_BK, TC_BM))) return rc;
+    if ((rc = make_tmap_2d(&tB_hi, w_hi, K, (uint64_t)P * TC_BN, K, TC_BK, TC_BN))) return rc;
+    if ((rc = make_tmap_2d(&tB_lo, w_lo, K, (uint64_t)P * TC_BN, K, TC_BK, TC_BN))) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(proj_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("proj_fwd_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_done = true;
+    }
+    ProjTcArgs a{gates + (long long)t_skip * B * TC_BN, b_ih, (long long)T * B * TC_BN, M, K};
+    dim3 grid((M + TC_BM - 1) / TC_BM, P);
+    proj_fwd_tc_kernel<<<grid, 192, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+    return check_launch("proj_fwd_tc_kernel");
+}

@@ -86,6 +86,12 @@ class CRVAEEngine:
         self.n_wih = P * G * p_
         self.rest_off = self.theta.offsets["w_hh"]
         self.col_norm = torch.zeros(P, p_, dtype=torch.float32, device=self.device)
+        # projection mode: "tc3" = tcgen05 3xTF32 (needs p % 4 == 0 for the TMA row pitch), "exact" = FFMA fp32
+        self.proj_mode = "tc3" if (p_ % 4 == 0 and hasattr(self.k, "proj_fwd_tc")) else "exact"
+        if self.proj_mode == "tc3":
+            zl = lambda t: torch.zeros_like(t)
+            self.w_ih_hi, self.w_ih_lo = zl(self.theta["w_ih"]), zl(self.theta["w_ih"])
+            self.enc_w_hi, self.enc_w_lo = zl(self.theta["enc_w_ih"]), zl(self.theta["enc_w_ih"])
         self.B = None
         self.kl_form = L.KL_SWAPPED
 
@@ -108,6 +114,12 @@ class CRVAEEngine:
         self.dec_in[1:].copy_(X[:, ENC_STEPS:-1].transpose(0, 1))                         # [Td,B,p], step 0 stays 0
         if self.P > 0:
             self.target[: self.P].copy_(X[:, ENC_STEPS:, lo:hi].permute(2, 1, 0))         # [P,Td,B]
+        if self.proj_mode == "tc3":      # the batch is fixed (:470-473): split it into tf32 hi/lo once
+            if getattr(self, "enc_in_hi", None) is None or self.enc_in_hi.shape != self.enc_in.shape:
+                self.enc_in_hi, self.enc_in_lo = torch.empty_like(self.enc_in), torch.empty_like(self.enc_in)
+                self.dec_in_hi, self.dec_in_lo = torch.empty_like(self.dec_in), torch.empty_like(self.dec_in)
+            self.k.split_tf32(self.enc_in, self.enc_in_hi, self.enc_in_lo, self.enc_in.numel())
+            self.k.split_tf32(self.dec_in, self.dec_in_hi, self.dec_in_lo, self.dec_in.numel())
 
     def _alloc(self, B: int):
         P, dev = self.P, self.device
@@ -152,7 +164,7 @@ class CRVAEEngine:
         if eps is not None:
             self.eps.copy_(eps.reshape(B, H), non_blocking=True)
         # encoder GRU (gru_left, :208) -> h_T
-        k.proj_fwd(self.enc_in, th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, ENC_STEPS, B, p_, 0)
+        self._project(self.enc_in, "enc", th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, ENC_STEPS, 0)
         k.gru_fwd(self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
                   self.enc_hs, self.enc_ghn, None, 1, ENC_STEPS, B, 0)
         hT = self.enc_hs[0, ENC_STEPS - 1]
@@ -161,7 +173,7 @@ class CRVAEEngine:
         k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, self.kl_form)
         # decoder heads (:218-219 -> GRU.forward :114-121): projection, recurrence (+Linear), MSE
         if P > 0:
-            k.proj_fwd(self.dec_in, th["w_ih"], th["b_ih"], self.gates, P, DEC_STEPS, B, p_, 1)
+            self._project(self.dec_in, "dec", th["w_ih"], th["b_ih"], self.gates, P, DEC_STEPS, 1)
             k.gru_fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
                       self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
             k.mse_fwd_bwd(self.pred, self.target, self.sse, self.dpred, self.err if want_err else None,
@@ -169,6 +181,17 @@ class CRVAEEngine:
             k.dot_small(self.sse, P, 1.0 / (DEC_STEPS * B), self.loss)
         else:
             self.loss.zero_()
+
+    def _project(self, x, which, w, b, gates, P, T, t_skip):
+        """gates = b + x . w^T for all heads / timesteps: tcgen05 3xTF32 GEMM or exact FFMA GEMM."""
+        k = self.k
+        if self.proj_mode == "tc3":
+            x_hi, x_lo = (self.enc_in_hi, self.enc_in_lo) if which == "enc" else (self.dec_in_hi, self.dec_in_lo)
+            w_hi, w_lo = (self.enc_w_hi, self.enc_w_lo) if which == "enc" else (self.w_ih_hi, self.w_ih_lo)
+            k.split_tf32(w, w_hi, w_lo, w.numel())          # weights change every iteration
+            k.proj_fwd_tc(x_hi, x_lo, w_hi, w_lo, b, gates, P, T, self.B, self.p, t_skip)
+        else:
+            k.proj_fwd(x, w, b, gates, P, T, self.B, self.p, t_skip)
 
     def forward_staged(self, want_err: bool = False):
         """forward() on the noise previously staged in self.eps_next (CUDA-graph friendly: the

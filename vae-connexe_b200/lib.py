@@ -25,6 +25,8 @@ SIGNATURES = {
     "crvae_gemm_f32": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_i64, _c_void_p, _c_int,
                                 _c_i64, _c_void_p, _c_int, _c_i64, _c_void_p, _c_i64, _c_int, _c_void_p]),
     "crvae_proj_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p]),
+    "crvae_proj_fwd_tc": (_c_int, [_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p]),
+    "crvae_split_tf32": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_void_p]),
     "crvae_proj_wgrad_workspace": (_c_size_t, [_c_int] * 4),
     "crvae_proj_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
     "crvae_gru_fwd": (_c_int, [_c_void_p] * 5 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
@@ -123,6 +125,13 @@ class Kernels:
     def proj_fwd(self, x, w_ih, b_ih, gates, P, T, B, K, t_skip):
         self._ck(self.lib.crvae_proj_fwd(ptr(x), ptr(w_ih), ptr(b_ih), ptr(gates), P, T, B, K, t_skip, stream_ptr()),
                  "crvae_proj_fwd")
+
+    def proj_fwd_tc(self, x_hi, x_lo, w_hi, w_lo, b_ih, gates, P, T, B, K, t_skip):
+        self._ck(self.lib.crvae_proj_fwd_tc(ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(b_ih), ptr(gates), P, T, B, K,
+                                            t_skip, stream_ptr()), "crvae_proj_fwd_tc")
+
+    def split_tf32(self, src, hi, lo, n):
+        self._ck(self.lib.crvae_split_tf32(ptr(src), ptr(hi), ptr(lo), n, stream_ptr()), "crvae_split_tf32")
 
     def proj_wgrad_workspace(self, P, T, B, K) -> int:
         return int(self.lib.crvae_proj_wgrad_workspace(P, T, B, K))
