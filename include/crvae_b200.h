@@ -87,6 +87,10 @@ int crvae_proj_fwd(const float* x, const float* w_ih, const float* b_ih, float* 
  * x_hi/x_lo [T,B,K], w_hi/w_lo [P,G,K].  Needs K % 4 == 0 (TMA row pitch).                    */
 int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
                       const float* b_ih, float* gates, int P, int T, int B, int K, int t_skip, void* stream);
+/* Tensor-core form of crvae_proj_wgrad (3xTF32, MN-major UMMA operands straight from the natural
+ * layouts; the gate gradients are split into tf32 hi/lo inside the kernel).  x_hi/x_lo [T,B,K].  */
+int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const float* x_lo, const uint8_t* mask,
+                        float* dw_ih, int P, int T, int B, int K, int t_skip, void* stream);
 /* hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i] (exact in fp32)               */
 int crvae_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);
 

@@ -90,6 +90,27 @@ def test_projection_tensor_core_3xtf32(P, T, B, K, t_skip):
     assert torch.equal(g[:, :t_skip].cpu(), torch.full((P, t_skip, B, G), 7.0))
 
 
+@pytest.mark.parametrize("P,T,B,K,t_skip", [(1, 10, 256, 100, 0), (3, 10, 64, 12, 1), (5, 10, 256, 100, 1), (2, 4, 40, 36, 1),
+                                            (100, 10, 256, 100, 1), (2, 10, 256, 1000, 1), (3, 10, 256, 200, 1)])
+def test_projection_wgrad_tensor_core_3xtf32(P, T, B, K, t_skip):
+    """tcgen05 weight gradient with MN-major operands + in-kernel tf32 split, against fp64."""
+    k = _k()
+    x, dg = _rand(T, B, K, seed=1), _rand(P, T, B, G, seed=5)
+    mask = (torch.rand(P, K, generator=torch.Generator().manual_seed(4)) < 0.6).to(torch.uint8)
+    ref = torch.einsum("ptbg,tbk->pgk", dg[:, t_skip:].double(), x[t_skip:].double())
+    xc = x.cuda()
+    xh, xl = torch.empty_like(xc), torch.empty_like(xc)
+    k.split_tf32(xc, xh, xl, xc.numel())
+    dgc = dg.cuda()
+    for m in (None, mask):
+        dw = torch.full((P, G, K), 3.0, device="cuda")
+        k.proj_wgrad_tc(dgc, xh, xl, None if m is None else m.cuda(), dw, P, T, B, K, t_skip)
+        torch.cuda.synchronize()
+        r = ref if m is None else ref * m[:, None, :].double()
+        assert _rel(dw, r) < 2e-5, (_rel(dw, r), P, K)
+    assert torch.equal(dgc.cpu(), dg)                      # the gate-gradient buffer itself is not modified
+
+
 @pytest.mark.parametrize("P,T,B,tile,lin,t_skip,shared_h0", [
     (3, 10, 64, 16, True, 1, True), (3, 10, 64, 32, True, 1, True), (3, 10, 64, 64, True, 1, True),
     (2, 10, 100, 64, True, 1, False), (1, 10, 256, 0, False, 0, True), (7, 3, 37, 32, True, 0, False),

@@ -79,6 +79,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// 4D tile load (coordinates innermost first)
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {   // one full warp
@@ -120,15 +128,18 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                           // layout type SWIZZLE_128B
     return d;
 }
-// MN-major tile: rows of 128 B hold 32 consecutive M/N elements for ONE k index; 8 k-rows form a
-// 1024-byte swizzle atom (SBO); the next 32 M/N elements start `lbo_bytes` further (LBO).
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major tf32 tile.  For 32-bit MN-major operands the only swizzled layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of
+// 128 B hold 32 consecutive M/N elements of ONE k index, 32-byte granules XOR-ed with (row mod 4); 4 k-rows
+// form a 512-byte atom (SBO = distance between 4-row groups); the next 32 M/N elements start `lbo_bytes`
+// further (LBO).  One K=8 MMA step consumes two atoms = 1024 B.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
+    d |= static_cast<uint64_t>(1) << 61;                           // layout type SWIZZLE_128B_BASE32B
     return d;
 }
 

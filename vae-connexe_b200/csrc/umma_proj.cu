@@ -165,7 +165,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // fp32 matrix [rows][inner] (inner contiguous, row stride = row_stride_elems), box {32 x box_rows}, 128B swizzle
 int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
-                 uint32_t box_inner, uint32_t box_rows) {
+                 uint32_t box_inner, uint32_t box_rows, bool atom32b) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return CRVAE_E_BADARG;
     cuuint64_t gdim[2] = {inner, rows};
@@ -173,11 +173,30 @@ int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t inner, uint64_t row
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu stride=%llu", (int)r, (unsigned long long)inner,
                   (unsigned long long)rows, (unsigned long long)row_stride_elems);
+        return CRVAE_E_BADARG;
+    }
+    return 0;
+}
+
+// general tiled map (rank <= 5), fp32, 128-byte swizzle; strides_bytes has rank-1 entries (dims 1..rank-1)
+int make_tmap_generic(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool atom32b) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return CRVAE_E_BADARG;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r);
         return CRVAE_E_BADARG;
     }
     return 0;
@@ -208,10 +227,10 @@ extern "C" int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const flo
     const long long xoff = (long long)t_skip * B * K;
     CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
     int rc;
-    if ((rc = make_tmap_2d(&tA_hi, x_hi + xoff, K, M, K, TC_BK, TC_BM))) return rc;
-    if ((rc = make_tmap_2d(&tA_lo, x_lo + xoff, K, M, K, TC_BK, TC_BM))) return rc;
-    if ((rc = make_tmap_2d(&tB_hi, w_hi, K, (uint64_t)P * TC_BN, K, TC_BK, TC_BN))) return rc;
-    if ((rc = make_tmap_2d(&tB_lo, w_lo, K, (uint64_t)P * TC_BN, K, TC_BK, TC_BN))) return rc;
+    if ((rc = make_tmap_2d(&tA_hi, x_hi + xoff, K, M, K, TC_BK, TC_BM, false))) return rc;
+    if ((rc = make_tmap_2d(&tA_lo, x_lo + xoff, K, M, K, TC_BK, TC_BM, false))) return rc;
+    if ((rc = make_tmap_2d(&tB_hi, w_hi, K, (uint64_t)P * TC_BN, K, TC_BK, TC_BN, false))) return rc;
+    if ((rc = make_tmap_2d(&tB_lo, w_lo, K, (uint64_t)P * TC_BN, K, TC_BK, TC_BN, false))) return rc;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(proj_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);

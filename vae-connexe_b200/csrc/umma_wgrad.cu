@@ -1,0 +1,199 @@
+// Weight gradient of the multi-head input projection on tcgen05 (autograd twin of umma_proj.cu):
+//
+//   dw_ih[i][g][k] = sum_{m = (t >= t_skip, b)} dgates[i][m][g] * x[m][k]        (CRVAE_lorenz96.py:497)
+//
+// (MN-major tf32 operands must use the SWIZZLE_128B_BASE32B shared-memory layout, which TMA produces with
+//  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.)
+// computed transposed, D[k][g] = X^T . dG, so that one accumulator tile is [128 input columns k
+// (TMEM lanes) x 192 gate rows g (TMEM columns)] and BOTH operands are consumed in their natural
+// global layouts as MN-major UMMA operands (the reduction index m is the slow index of x [m][k]
+// and of dgates [m][g]): no transposed copy of the 196 MB gate-gradient buffer is ever made.
+//
+//   warp 0   : TMA producer.  A = x_hi / x_lo (the fixed batch, pre-split once) as 4+4 boxes
+//              {32 k x 32 m}; B = raw fp32 dgates as ONE 4-D box {32 g, 32 m, 6 g-blocks, head}.
+//   warps 2-5: converter: split the landed dgates tile into tf32 hi (in place) and lo (second
+//              buffer) in shared memory -- the swizzled layout is preserved because the split is
+//              element-wise -- then fence.proxy.async + arrive; afterwards they are the epilogue.
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, 3xTF32 per 8-row K step.
+// One CTA owns one (k-tile, head) pair and walks all row chunks; smem ring 2 x 80 KB.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace crvae {
+
+int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+                 uint32_t box_inner, uint32_t box_rows, bool atom32b);
+int make_tmap_generic(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool atom32b);
+
+constexpr int WG_BM = 128;                 // input columns k per tile (UMMA M, TMEM lanes)
+constexpr int WG_BN = CRVAE_G;             // 192 gate rows (UMMA N, TMEM columns)
+constexpr int WG_BK = 32;                  // reduction rows (m) per stage
+constexpr int WG_STAGES = 2;
+constexpr int WG_A_BYTES = WG_BM * WG_BK * 4;          // 16384: 4 MN-blocks x [32 rows x 128 B]
+constexpr int WG_B_BYTES = WG_BN * WG_BK * 4;          // 24576: 6 MN-blocks x [32 rows x 128 B]
+constexpr int WG_BLOCK_BYTES = WG_BK * 128;            // 4096: one MN-block (32 M/N elements) of a stage = LBO
+constexpr int WG_STAGE_BYTES = 2 * WG_A_BYTES + 2 * WG_B_BYTES;
+constexpr int WG_TX_BYTES = 2 * WG_A_BYTES + WG_B_BYTES;   // bytes landed by TMA per stage (B_lo is produced in smem)
+constexpr int WG_TMEM_COLS = 256;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+struct WgradTcArgs {
+    float* dW;               // [P][G][K]
+    const uint8_t* mask;     // [P][K] or null
+    int K, R, row_off;       // R = rows reduced per head (starting at row_off within the head's T*B rows)
+};
+
+__global__ void __launch_bounds__(192, 1)
+proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                     const __grid_constant__ CUtensorMap tmG, WgradTcArgs a) {
+    using namespace umma;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* conv = full + WG_STAGES;
+    uint64_t* empty = conv + WG_STAGES;
+    uint64_t* tmem_full = empty + WG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k_tile = blockIdx.x, head = blockIdx.y;
+    const int nchunks = (a.R + WG_BK - 1) / WG_BK;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmX_hi); prefetch_tmap(&tmX_lo); prefetch_tmap(&tmG); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
+            mbar_init(tmem_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<WG_TMEM_COLS>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % WG_STAGES, ph = (c / WG_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * WG_STAGE_BYTES;
+                const int row = a.row_off + c * WG_BK;
+                mbar_arrive_expect_tx(&full[s], WG_TX_BYTES);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tma_load_2d(st + j * WG_BLOCK_BYTES, &tmX_hi, &full[s], k_tile * WG_BM + 32 * j, row);
+                    tma_load_2d(st + WG_A_BYTES + j * WG_BLOCK_BYTES, &tmX_lo, &full[s], k_tile * WG_BM + 32 * j, row);
+                }
+                tma_load_4d(st + 2 * WG_A_BYTES, &tmG, &full[s], 0, row, 0, head);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(WG_BM, WG_BN, true, true);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % WG_STAGES, ph = (c / WG_STAGES) & 1;
+                mbar_wait(&conv[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * WG_STAGE_BYTES);
+                const uint64_t a_hi = smem_desc_mn_sw128_32b(st, WG_BLOCK_BYTES), a_lo = smem_desc_mn_sw128_32b(st + WG_A_BYTES, WG_BLOCK_BYTES);
+                const uint64_t b_hi = smem_desc_mn_sw128_32b(st + 2 * WG_A_BYTES, WG_BLOCK_BYTES);
+                const uint64_t b_lo = smem_desc_mn_sw128_32b(st + 2 * WG_A_BYTES + WG_B_BYTES, WG_BLOCK_BYTES);
+                int ksteps = (a.R - c * WG_BK + 7) / 8;
+                if (ksteps > WG_BK / 8) ksteps = WG_BK / 8;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t adv = static_cast<uint64_t>(k * (1024 >> 4));   // next 8 reduction rows = next 1024-byte atom
+                    mma_tf32_ss(tmem_base, a_lo + adv, b_hi + adv, idesc, (c | k) != 0);
+                    mma_tf32_ss(tmem_base, a_hi + adv, b_lo + adv, idesc, true);
+                    mma_tf32_ss(tmem_base, a_hi + adv, b_hi + adv, idesc, true);
+                }
+                mma_commit(&empty[s]);
+            }
+            mma_commit(tmem_full);
+        }
+    } else {
+        const int cw = warp - 2;                     // converter warp 0..3
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % WG_STAGES, ph = (c / WG_STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            float4* hi = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + 2 * WG_A_BYTES);
+            float4* lo = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + 2 * WG_A_BYTES + WG_B_BYTES);
+#pragma unroll 4
+            for (int e = cw * 32 + lane; e < WG_B_BYTES / 16; e += 128) {
+                float4 v = hi[e];
+                float4 h, l;
+                uint32_t t;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = __fsub_rn(v.x, h.x);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = __fsub_rn(v.y, h.y);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = __fsub_rn(v.z, h.z);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = __fsub_rn(v.w, h.w);
+                hi[e] = h;
+                lo[e] = l;
+            }
+            fence_proxy_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&conv[s]);
+        }
+        // epilogue: D[lane = k][col = g] -> dW[head][g][k]   (coalesced over lanes for every g)
+        const int q = warp & 3;
+        const int kcol = k_tile * WG_BM + q * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        float mval = 1.f;
+        if (a.mask && kcol < a.K) mval = a.mask[static_cast<long long>(head) * a.K + kcol] ? 1.f : 0.f;
+        float* out = a.dW + static_cast<long long>(head) * WG_BN * a.K + kcol;
+#pragma unroll 1
+        for (int c0 = 0; c0 < WG_BN; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), v);
+            tmem_ld_wait();
+            if (kcol < a.K) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) out[static_cast<long long>(c0 + j) * a.K] = v[j] * mval;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<WG_TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace crvae
+
+using namespace crvae;
+
+extern "C" int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const float* x_lo, const uint8_t* mask,
+                                   float* dw_ih, int P, int T, int B, int K, int t_skip, void* stream) {
+    CRVAE_REQUIRE(dgates && x_hi && x_lo && dw_ih, "null operand");
+    CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0 && K > 0 && t_skip >= 0 && t_skip <= T, "bad size");
+    CRVAE_REQUIRE(K % 4 == 0, "tensor-core weight gradient needs K % 4 == 0 (16-byte TMA row pitch); use crvae_proj_wgrad");
+    CRVAE_REQUIRE(aligned16(dgates) && aligned16(x_hi) && aligned16(x_lo), "16-byte alignment");
+    if (P == 0) return 0;
+    const int R = (T - t_skip) * B;
+    if (R == 0) return (int)cudaMemsetAsync(dw_ih, 0, (size_t)P * CRVAE_G * K * sizeof(float), (cudaStream_t)stream);
+    CUtensorMap tX_hi, tX_lo, tG;
+    int rc;
+    if ((rc = make_tmap_2d(&tX_hi, x_hi, K, (uint64_t)T * B, K, 32, WG_BK, true))) return rc;
+    if ((rc = make_tmap_2d(&tX_lo, x_lo, K, (uint64_t)T * B, K, 32, WG_BK, true))) return rc;
+    // dgates [P][T*B][192] viewed as {32 g_in, T*B rows, 6 g-blocks, P heads}; box {32, 32, 6, 1}
+    const uint64_t dims[4] = {32, (uint64_t)T * B, 6, (uint64_t)P};
+    const uint64_t strides[3] = {(uint64_t)CRVAE_G * 4, 128, (uint64_t)T * B * CRVAE_G * 4};
+    const uint32_t box[4] = {32, WG_BK, 6, 1};
+    if ((rc = make_tmap_generic(&tG, dgates, 4, dims, strides, box, true))) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(proj_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("proj_wgrad_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_done = true;
+    }
+    WgradTcArgs a{dw_ih, mask, K, R, t_skip * B};
+    dim3 grid((K + WG_BM - 1) / WG_BM, P);
+    proj_wgrad_tc_kernel<<<grid, 192, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tX_hi, tX_lo, tG, a);
+    return check_launch("proj_wgrad_tc_kernel");
+}

@@ -87,7 +87,7 @@ class CRVAEEngine:
         self.rest_off = self.theta.offsets["w_hh"]
         self.col_norm = torch.zeros(P, p_, dtype=torch.float32, device=self.device)
         # projection mode: "tc3" = tcgen05 3xTF32 (needs p % 4 == 0 for the TMA row pitch), "exact" = FFMA fp32
-        self.proj_mode = "tc3" if (p_ % 4 == 0 and hasattr(self.k, "proj_fwd_tc")) else "exact"
+        self.proj_mode = "tc3" if (p_ % 4 == 0 and hasattr(self.k, "proj_wgrad_tc")) else "exact"
         if self.proj_mode == "tc3":
             zl = lambda t: torch.zeros_like(t)
             self.w_ih_hi, self.w_ih_lo = zl(self.theta["w_ih"]), zl(self.theta["w_ih"])
@@ -206,7 +206,10 @@ class CRVAEEngine:
         if P > 0:
             k.gru_bwd(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
                       g["w_hh"], g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
-            k.proj_wgrad(self.gates, self.dec_in, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1, self.ws_wgrad)
+            if self.proj_mode == "tc3":
+                k.proj_wgrad_tc(self.gates, self.dec_in_hi, self.dec_in_lo, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1)
+            else:
+                k.proj_wgrad(self.gates, self.dec_in, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1, self.ws_wgrad)
             if lam_ridge != 0.0:      # d/dW of lam*(|linear.W|^2 + |W_hh|^2), ridge_regularize :321-325
                 k.axpy(g["w_hh"], th["w_hh"], P * G * H, 2.0 * lam_ridge)
                 k.axpy(g["w_lin"], th["w_lin"], P * H, 2.0 * lam_ridge)

@@ -26,6 +26,7 @@ SIGNATURES = {
                                 _c_i64, _c_void_p, _c_int, _c_i64, _c_void_p, _c_i64, _c_int, _c_void_p]),
     "crvae_proj_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p]),
     "crvae_proj_fwd_tc": (_c_int, [_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p]),
+    "crvae_proj_wgrad_tc": (_c_int, [_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p]),
     "crvae_split_tf32": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_void_p]),
     "crvae_proj_wgrad_workspace": (_c_size_t, [_c_int] * 4),
     "crvae_proj_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
@@ -129,6 +130,10 @@ class Kernels:
     def proj_fwd_tc(self, x_hi, x_lo, w_hi, w_lo, b_ih, gates, P, T, B, K, t_skip):
         self._ck(self.lib.crvae_proj_fwd_tc(ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(b_ih), ptr(gates), P, T, B, K,
                                             t_skip, stream_ptr()), "crvae_proj_fwd_tc")
+
+    def proj_wgrad_tc(self, dgates, x_hi, x_lo, mask, dw_ih, P, T, B, K, t_skip):
+        self._ck(self.lib.crvae_proj_wgrad_tc(ptr(dgates), ptr(x_hi), ptr(x_lo), ptr(mask), ptr(dw_ih), P, T, B, K, t_skip,
+                                              stream_ptr()), "crvae_proj_wgrad_tc")
 
     def split_tf32(self, src, hi, lo, n):
         self._ck(self.lib.crvae_split_tf32(ptr(src), ptr(hi), ptr(lo), n, stream_ptr()), "crvae_split_tf32")
