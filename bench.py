@@ -227,6 +227,8 @@ def run_ours(args):
     m = V.CRVAE(p_total, np.ones((p_total, p_total)), 64, rank=rank, world_size=world, group=group)
     eng = m.engine
     lr, lam = 5e-2, 0.1
+    if os.environ.get("CRVAE_BATCH_TILE"):
+        eng.k.set_batch_tile(int(os.environ["CRVAE_BATCH_TILE"]))
     run = V.Phase1Runner(m, Xb.to(dev), lr, lam, 0.0, 0.1, use_graphs=not args.no_graphs)
     n_eps = 16
     gen = torch.Generator().manual_seed(1234)

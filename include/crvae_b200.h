@@ -181,6 +181,17 @@ int crvae_gd_prox_gc(float* w_ih, const float* dw_ih, const uint8_t* mask, float
 int crvae_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                     double lr, double beta1, double beta2, double eps, int step, void* stream);
 
+/* y = tanh(x) and its backward dx = dy*(1-y^2): VRAE4E's z = tanh(linear_hidden(z)) (:164)         */
+int crvae_tanh_fwd(const float* x, float* y, int64_t n, void* stream);
+int crvae_tanh_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+/* out[c][r] = in[r][c]: residual [P][T*B] (head-major) <-> [T*B][P] (VRAE4E input, :599/:639)       */
+int crvae_transpose(const float* in, float* out, int rows, int cols, void* stream);
+
+/* Same update with the step count in device memory (step = *step_counter + 1, then incremented):
+ * lets the whole phase-2 iteration be replayed from a CUDA graph.                                  */
+int crvae_adam_step_dev(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        double lr, double beta1, double beta2, double eps, int* step_counter, void* stream);
+
 /* Ridge penalty pieces (ridge_regularize :321-325): out[0] = sum(x^2) over n elements.          */
 int crvae_sumsq(const float* x, int64_t n, float* out, void* stream);
 /* out[0] = sum_i scale[i] * x[i] for n <= 4096 values (loss = sum_i sse[i]/(T*B) and friends)     */

@@ -371,3 +371,114 @@ def train_phase1(prm: Params, X_series: Tensor, context: int, lr: float, max_ite
             prm[k] = best[k]
     prm["_best_it"] = torch.tensor(-1 if best_it is None else best_it)
     return prm
+
+
+# ----------------------------------------------------------------------------------------------
+# VRAE4E -- the error-compensation VRAE of phase 2  (CRVAE_lorenz96.py:123-179, :599-603, :639-643)
+# parameters: enc_w_ih [G,p] enc_w_hh [G,H] enc_b_ih enc_b_hh [G]   (gru_left :133)
+#             mu_w mu_b std_w std_b (fc_mu/fc_std :136-137)  hid_w [H,H] hid_b [H] (linear_hidden :139)
+#             dec_w_ih [G,p] dec_w_hh [G,H] dec_b_ih dec_b_hh [G]   (gru :142)   out_w [p,H] out_b [p] (linear :144)
+# ----------------------------------------------------------------------------------------------
+VRAE_KEYS = ("enc_w_ih", "enc_w_hh", "enc_b_ih", "enc_b_hh", "mu_w", "mu_b", "std_w", "std_b", "hid_w", "hid_b",
+             "dec_w_ih", "dec_w_hh", "dec_b_ih", "dec_b_hh", "out_w", "out_b")
+_VRAE_SD = ("gru_left.weight_ih_l0", "gru_left.weight_hh_l0", "gru_left.bias_ih_l0", "gru_left.bias_hh_l0",
+            "fc_mu.weight", "fc_mu.bias", "fc_std.weight", "fc_std.bias", "linear_hidden.weight", "linear_hidden.bias",
+            "gru.weight_ih_l0", "gru.weight_hh_l0", "gru.bias_ih_l0", "gru.bias_hh_l0", "linear.weight", "linear.bias")
+
+
+def vrae_params_from_state_dict(sd: Dict[str, Tensor], dtype=torch.float32) -> Params:
+    return {k: sd[s].detach().to(dtype).clone().contiguous() for k, s in zip(VRAE_KEYS, _VRAE_SD)}
+
+
+def vrae_state_dict_from_params(prm: Params) -> Dict[str, Tensor]:
+    return {s: prm[k].clone() for k, s in zip(VRAE_KEYS, _VRAE_SD)}
+
+
+def vrae_forward(prm: Params, err: Tensor, eps: Tensor) -> Dict[str, Tensor]:
+    """err (B,10,p) = the detached residual (:599); eps (B,H) the draw of :161."""
+    dt = prm["enc_w_hh"].dtype
+    err = err.to(dt)
+    B = err.shape[0]
+    Hh = prm["enc_w_hh"].shape[1]
+    eps = eps.to(dt).reshape(B, Hh)
+    enc_in = err.transpose(0, 1).contiguous()                                             # X'[:,1:] (:155)
+    dec_in = torch.cat([torch.zeros_like(err[:, :1]), err[:, :-1]], 1).transpose(0, 1).contiguous()   # X'[:,:-1] (:166)
+    gi_e = (enc_in @ prm["enc_w_ih"].t() + prm["enc_b_ih"]).unsqueeze(0)
+    ehs, er, ez, en, eghn = gru_forward(gi_e, torch.zeros(B, Hh, dtype=dt), prm["enc_w_hh"][None], prm["enc_b_hh"][None])
+    hT = ehs[0, -1]
+    mu = hT @ prm["mu_w"].t() + prm["mu_b"]                  # :157
+    log_var = hT @ prm["std_w"].t() + prm["std_b"]           # :158
+    sigma = torch.exp(0.5 * log_var)
+    zlat = mu + sigma * eps                                  # :160-163
+    zh = torch.tanh(zlat @ prm["hid_w"].t() + prm["hid_b"])  # :164
+    gi_d = (dec_in @ prm["dec_w_ih"].t() + prm["dec_b_ih"]).unsqueeze(0)
+    dhs, dr, dz, dn, dghn = gru_forward(gi_d, zh, prm["dec_w_hh"][None], prm["dec_b_hh"][None])
+    pred = dhs[0, 1:] @ prm["out_w"].t() + prm["out_b"]      # [Td,B,p]  (:167)
+    return dict(enc_in=enc_in, dec_in=dec_in, eps=eps, ehs=ehs, er=er, ez=ez, en=en, eghn=eghn, hT=hT, mu=mu,
+                log_var=log_var, sigma=sigma, zlat=zlat, zh=zh, dhs=dhs, dr=dr, dz=dz, dn=dn, dghn=dghn, pred=pred,
+                target=enc_in)
+
+
+def vrae_loss(act: Dict[str, Tensor], beta_e: float = 1.0):
+    """loss_e = MSE(pred_e, error) (:601); KL with the same swapped names as the CRVAE trainer (:600-602)."""
+    diff = act["pred"] - act["target"]
+    loss = (diff * diff).mean()
+    a, s = act["mu"], act["log_var"]
+    kl = (-0.5 * (1 + a - s * s - torch.exp(a))).sum(-1).mean(0)
+    return dict(loss=loss, kl=kl, smooth=loss + beta_e * kl, diff=diff)
+
+
+def vrae_backward(prm: Params, act: Dict[str, Tensor], lossd: Dict[str, Tensor], beta_e: float = 1.0) -> Params:
+    Td, B, p = act["pred"].shape
+    dpred = 2.0 * lossd["diff"] / (Td * B * p)
+    g: Params = {}
+    hs_out = act["dhs"][0, 1:]
+    g["out_w"] = torch.einsum("tbp,tbh->ph", dpred, hs_out)
+    g["out_b"] = dpred.sum((0, 1))
+    dh_out = (dpred @ prm["out_w"])[None]
+    dgi_d, dw, db, dh0 = gru_backward(dh_out, act["dhs"], act["dr"], act["dz"], act["dn"], act["dghn"], prm["dec_w_hh"][None])
+    g["dec_w_ih"] = torch.einsum("tbg,tbk->gk", dgi_d[0], act["dec_in"])
+    g["dec_b_ih"] = dgi_d[0].sum((0, 1))
+    g["dec_w_hh"], g["dec_b_hh"] = dw[0], db[0]
+    dpre = dh0[0] * (1 - act["zh"] * act["zh"])
+    g["hid_w"] = dpre.t() @ act["zlat"]
+    g["hid_b"] = dpre.sum(0)
+    dzlat = dpre @ prm["hid_w"]
+    a, s = act["mu"], act["log_var"]
+    dmu = dzlat + beta_e * (-0.5 * (1 - torch.exp(a))) / B
+    dlv = dzlat * act["eps"] * 0.5 * act["sigma"] + beta_e * s / B
+    g["mu_w"] = dmu.t() @ act["hT"]; g["mu_b"] = dmu.sum(0)
+    g["std_w"] = dlv.t() @ act["hT"]; g["std_b"] = dlv.sum(0)
+    dhT = dmu @ prm["mu_w"] + dlv @ prm["std_w"]
+    Te = act["er"].shape[1]
+    zero = torch.zeros(1, Te, B, dhT.shape[-1], dtype=dhT.dtype)
+    dgi_e, dw, db, _ = gru_backward(zero, act["ehs"], act["er"], act["ez"], act["en"], act["eghn"], prm["enc_w_hh"][None],
+                                    dh_last=dhT[None])
+    g["enc_w_ih"] = torch.einsum("tbg,tbk->gk", dgi_e[0], act["enc_in"])
+    g["enc_b_ih"] = dgi_e[0].sum((0, 1))
+    g["enc_w_hh"], g["enc_b_hh"] = dw[0], db[0]
+    return g
+
+
+def crvae_error(act: Dict[str, Tensor]) -> Tensor:
+    """error = X[:,10:,:] - stack(pred)[...,0].permute(1,2,0)  (B,10,p), detached (:599/:639)."""
+    return (act["target"] - act["pred"].permute(1, 2, 0)).permute(1, 0, 2).contiguous()
+
+
+def phase2_iteration(prm: Params, vprm: Params, adam_state: dict, step: int, X: Tensor, eps_c: Tensor, eps_e: Tensor,
+                     lr: float, lam: float = 0.0, lam_ridge: float = 0.0):
+    """forward both models -> losses -> Adam on the VRAE (:611-614) -> GD (+prox) on the CRVAE (:616-623).
+    beta = beta_e = 1 (:582-583).  `step` counts Adam steps from 1."""
+    act = crvae_forward(prm, X, eps_c)
+    lossd = crvae_loss(prm, act, lam_ridge, 1.0)
+    err = crvae_error(act)
+    vact = vrae_forward(vprm, err, eps_e)
+    vloss = vrae_loss(vact, 1.0)
+    vgrads = vrae_backward(vprm, vact, vloss, 1.0)
+    if lam == 0:
+        adam_step(vprm, vgrads, adam_state, step)
+    grads = crvae_backward(prm, act, lossd, lam_ridge, 1.0)
+    gd_step(prm, grads, lr)
+    if lam > 0:
+        prm["w_ih"] = prox_update(prm["w_ih"], lam, lr)
+    return dict(act=act, lossd=lossd, grads=grads, err=err, vact=vact, vloss=vloss, vgrads=vgrads)

@@ -181,6 +181,20 @@ class OracleKernels:
         th.addcdiv_(mm, denom, value=-(lr / bc1))
         self.launches += 1
 
+    def adam_step_dev(self, theta, grad, m, v, n, lr, b1, b2, eps, counter):
+        self.adam_step(theta, grad, m, v, n, lr, b1, b2, eps, int(counter[0]) + 1)
+        counter[0] += 1
+
+    def tanh_fwd(self, x, y, n):
+        y.reshape(-1)[:n] = torch.tanh(x.reshape(-1)[:n]); self.launches += 1
+
+    def tanh_bwd(self, dy, y, dx, n):
+        dx.reshape(-1)[:n] = dy.reshape(-1)[:n] * (1 - y.reshape(-1)[:n] ** 2); self.launches += 1
+
+    def transpose(self, src, dst, rows, cols):
+        dst.reshape(-1)[: rows * cols].view(cols, rows).copy_(src.reshape(-1)[: rows * cols].view(rows, cols).t())
+        self.launches += 1
+
     def sumsq(self, x, n, out):
         out[0] = (x.reshape(-1)[:n] ** 2).sum()
         self.launches += 1

@@ -290,3 +290,94 @@ def test_ragged_heads_iteration_matches_oracle():
         assert _rel(post[k], prm[k]) < TOL, k
     assert torch.equal(post["w_ih"][~prm["mask"]][:, None].expand(-1, 1).flatten() if False else
                        (post["w_ih"] * (~prm["mask"])[:, None, :].float()).abs().sum(), torch.tensor(0.0))
+
+
+@pytest.fixture(scope="module")
+def ph2():
+    return np.load(os.path.join(GOLDEN, "p10_phase2.npz"))
+
+
+def _vrae_tensors(arena):
+    out = {k: arena[k].detach().cpu() for k in ("enc_w_ih", "enc_w_hh", "enc_b_ih", "enc_b_hh", "hid_w", "hid_b", "dec_w_ih",
+                                                 "dec_w_hh", "dec_b_ih", "dec_b_hh", "out_w", "out_b")}
+    out["mu_w"], out["std_w"] = arena["lat_w"][:H].cpu(), arena["lat_w"][H:].cpu()
+    out["mu_b"], out["std_b"] = arena["lat_b"][:H].cpu(), arena["lat_b"][H:].cpu()
+    return out
+
+
+def test_phase2_iteration_matches_reference_golden(ph2, traj):
+    """Pruned CRVAE (ragged heads from the golden GC) + VRAE4E + Adam: residual, both losses, every
+    gradient and the updated weights of the reference's first phase-2 iteration."""
+    import vae_connexe_b200 as V
+    GC = ph2["connection"]
+    torch.manual_seed(0); np.random.seed(0)
+    cg, vr = V.CRVAE(10, GC, 64), V.VRAE4E(10, 64)
+    wins = O.arrange_input(torch.from_numpy(traj["data"].T.copy()), 20)[0]
+    X = wins[ph2["idx"]].cuda()
+    run = V.Phase2Runner(cg, vr, X, 5e-2, 0.0, 0.0, use_graphs=False)
+    run.forward(torch.from_numpy(ph2["eps_c"]).cuda(), torch.from_numpy(ph2["eps_e"]).cuda())
+    ce, ve = cg.engine, vr.engine
+    assert abs(float(ce.loss) - float(ph2["loss"])) < TOL * float(ph2["loss"])
+    assert abs(float(ce.kl) - float(ph2["kl"])) < TOL * float(ph2["kl"])
+    assert _rel(ce.err_tbp.permute(1, 0, 2), ph2["error"]) < TOL
+    assert _rel(ve.pred.permute(1, 0, 2), ph2["pred_e"]) < TOL
+    assert abs(float(ve.loss) - float(ph2["loss_e"])) < TOL * float(ph2["loss_e"])
+    assert abs(float(ve.kl) - float(ph2["kl_e"])) < TOL * float(ph2["kl_e"])
+    run.update()
+    vg, cgr = _vrae_tensors(ve.grad), _engine_tensors(ce.grad)
+    for k in O.VRAE_KEYS:
+        assert _rel(vg[k], ph2["v_grad." + k]) < TOL, k
+    for k in O.PARAM_KEYS:
+        assert _rel(cgr[k], ph2["c_grad." + k]) < TOL, k
+    vp, cp = _vrae_tensors(ve.theta), _engine_tensors(ce.theta)
+    for k in O.VRAE_KEYS:
+        assert _rel(vp[k], ph2["v_post." + k]) < TOL, k
+    for k in O.PARAM_KEYS:
+        assert _rel(cp[k], ph2["c_post." + k]) < TOL, k
+    assert float((cp["w_ih"] * (~torch.from_numpy(ph2["c_init.mask"]))[:, None, :].float()).abs().sum()) == 0.0
+
+
+def test_train_phase2_tracks_golden_log(ph2, traj):
+    import vae_connexe_b200 as V
+    GC = ph2["connection"]
+    Xt = torch.from_numpy(traj["data"].T.copy())[None].cuda()
+    torch.manual_seed(0); np.random.seed(0)
+    cg, vr = V.CRVAE(10, GC, 64), V.VRAE4E(10, 64)
+    log = []
+    V.train_phase2(cg, vr, Xt, context=20, lam=0., lam_ridge=0, lr=5e-2, max_iter=21, check_every=10, verbose=0, log=log)
+    assert [r["it"] for r in log] == list(ph2["log_it"])
+    for i, r in enumerate(log):
+        for key, gold in (("mean_loss", "log_loss"), ("kl", "log_kl"), ("loss_e", "log_loss_e"), ("kl_e", "log_kl_e")):
+            assert abs(r[key] - ph2[gold][i]) < TOL * abs(ph2[gold][i]) + 2e-6, (i, key, r[key], ph2[gold][i])
+    vp, cp = _vrae_tensors(vr.engine.theta), _engine_tensors(cg.engine.theta)
+    for k in O.VRAE_KEYS:
+        assert _rel(vp[k], ph2["v_final." + k]) < 5 * TOL, k
+    for k in O.PARAM_KEYS:
+        assert _rel(cp[k], ph2["c_final." + k]) < 5 * TOL, k
+    assert np.array_equal(torch.get_rng_state().numpy(), ph2["rng_after"])
+
+
+def test_generation_gpu_matches_checker_backend():
+    """Test-mode generation (CRVAE phase 0/1, VRAE4E): the same host code on the CUDA kernels and on the
+    CPU checker backend (which is checked against the live reference in tests/test_host_logic.py)."""
+    import vae_connexe_b200 as V
+    import vae_connexe_b200.lib as L
+    from tests.cpu_backend import OracleKernels
+    p, B = 8, 32
+    torch.manual_seed(3)
+    m, v = V.CRVAE(p, np.ones((p, p)), 64), V.VRAE4E(p, 64)
+    prev = L._kernels
+    L.set_test_backend(OracleKernels())
+    try:
+        torch.manual_seed(3)
+        mc, vc = V.CRVAE(p, np.ones((p, p)), 64), V.VRAE4E(p, 64)
+        X, err = torch.randn(B, 20, p), torch.randn(B, 10, p)
+        st = torch.get_rng_state()
+        a0, a1 = mc(X, mode="test"), vc(err, mode="test")
+        a2 = mc(X, a1[:, 1:], mode="test", phase=1)
+    finally:
+        L.set_test_backend(prev)
+    torch.set_rng_state(st)
+    b0, b1 = m(X.cuda(), mode="test"), v(err.cuda(), mode="test")
+    b2 = m(X.cuda(), a1[:, 1:].cuda(), mode="test", phase=1)
+    assert _rel(b0, a0) < TOL and _rel(b1, a1) < TOL and _rel(b2, a2) < TOL

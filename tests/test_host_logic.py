@@ -170,3 +170,102 @@ def test_ragged_init_matches_reference_order(cpu_backend):
         rest = np.setdiff1d(np.arange(p), cols)
         assert float(dense[:, rest].abs().sum()) == 0.0
     assert m.networks[0].p == int(conn[:, 0].sum())
+
+
+@pytest.fixture(scope="module")
+def ph2():
+    return np.load(os.path.join(GOLDEN, "p10_phase2.npz"))
+
+
+def test_vrae4e_surface_and_init(cpu_backend, ph2):
+    import vae_connexe_b200 as V
+    GC = ph2["connection"]
+    torch.manual_seed(0); np.random.seed(0)
+    cg = V.CRVAE(10, GC, 64)
+    vr = V.VRAE4E(10, 64)
+    names = [n for n, _ in vr.named_parameters()]
+    assert names == ["gru_left.weight_ih_l0", "gru_left.weight_hh_l0", "gru_left.bias_ih_l0", "gru_left.bias_hh_l0",
+                     "fc_mu.weight", "fc_mu.bias", "fc_std.weight", "fc_std.bias", "linear_hidden.weight", "linear_hidden.bias",
+                     "gru.weight_ih_l0", "gru.weight_hh_l0", "gru.bias_ih_l0", "gru.bias_hh_l0", "linear.weight", "linear.bias"]
+    vp = O.vrae_params_from_state_dict({k: v for k, v in vr.named_parameters()})
+    for k in O.VRAE_KEYS:
+        assert np.array_equal(vp[k].numpy(), ph2["v_init." + k]), k              # same seed -> the reference's VRAE4E init
+    cp = O.params_from_state_dict(cg.state_dict(), GC)
+    for k in O.PARAM_KEYS:
+        assert np.array_equal(cp[k].numpy(), ph2["c_init." + k]), k              # pruned CRVAE init (ragged heads)
+
+
+def test_train_phase2_tracks_reference_log(cpu_backend, ph2, traj):
+    """train_phase2 host logic (Adam on the VRAE, GD on the pruned CRVAE, draw order incl. the unused
+    numpy draw of :628 and the two generation draws per check) against the reference's 21-iteration run."""
+    import vae_connexe_b200 as V
+    GC = ph2["connection"]
+    Xt = torch.from_numpy(traj["data"].T.copy())[None]
+    torch.manual_seed(0); np.random.seed(0)
+    cg = V.CRVAE(10, GC, 64)
+    vr = V.VRAE4E(10, 64)
+    log = []
+    out = V.train_phase2(cg, vr, Xt, context=20, lam=0., lam_ridge=0, lr=5e-2, max_iter=21, check_every=10, verbose=0, log=log)
+    assert out == [] and [r["it"] for r in log] == list(ph2["log_it"])
+    for i, r in enumerate(log):
+        assert abs(r["mean_loss"] - ph2["log_loss"][i]) < 3e-6 and abs(r["kl"] - ph2["log_kl"][i]) < 3e-6
+        assert abs(r["loss_e"] - ph2["log_loss_e"][i]) < 3e-6 and abs(r["kl_e"] - ph2["log_kl_e"][i]) < 3e-6
+    vp = O.vrae_params_from_state_dict({k: v for k, v in vr.named_parameters()})
+    for k in O.VRAE_KEYS:
+        assert _rel(vp[k], ph2["v_final." + k]) < 2e-5, k
+    cp = O.params_from_state_dict(cg.state_dict(), GC)
+    for k in O.PARAM_KEYS:
+        assert _rel(cp[k], ph2["c_final." + k]) < 2e-5, k
+    assert np.array_equal(torch.get_rng_state().numpy(), ph2["rng_after"])      # torch generator where the reference left it
+    assert np.random.randint(1 << 30) == int(ph2["np_rng_after_draw"])          # numpy generator too (:628 draws)
+
+
+def test_test_mode_generation_shapes_and_rng(cpu_backend):
+    import vae_connexe_b200 as V
+    torch.manual_seed(1)
+    m = V.CRVAE(6, np.ones((6, 6)), 64)
+    vr = V.VRAE4E(6, 64)
+    X = torch.randn(8, 20, 6)
+    st = torch.get_rng_state()
+    seq = m(X, mode="test")
+    assert seq.shape == (8, 21, 6)
+    nxt = torch.randn(3)
+    torch.set_rng_state(st); torch.randn(size=(1, 8, 64))
+    assert torch.equal(nxt, torch.randn(3))                 # exactly one (1,B,H) draw consumed (:225)
+    e = vr(torch.randn(8, 10, 6), mode="test")
+    assert e.shape == (8, 22, 6) and float(e[:, 0].abs().sum()) == 0.0
+    seq1 = m(X, e[:, 1:], mode="test", phase=1)
+    assert seq1.shape == (8, 21, 6)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).reference_available(),
+                    reason="reference tree only exists in the build container")
+def test_generation_matches_live_reference(cpu_backend):
+    """Test-mode generation (CRVAE phase 0 / phase 1, VRAE4E) against the reference's own modules with
+    identical weights and generator state."""
+    import vae_connexe_b200 as V
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    p, B = 5, 16
+    conn = np.ones((p, p))
+    torch.manual_seed(7)
+    rm, rv = ref.CRVAE(p, conn, 64), ref.VRAE4E(p, 64)
+    torch.manual_seed(7)
+    m, v = V.CRVAE(p, conn, 64), V.VRAE4E(p, 64)
+    X = torch.randn(B, 20, p)
+    err = torch.randn(B, 10, p)
+    for fn_ref, fn_new in ((lambda: rm(X, mode="test"), lambda: m(X, mode="test")),
+                           (lambda: rv(err, mode="test"), lambda: v(err, mode="test"))):
+        st = torch.get_rng_state()
+        a = fn_ref().detach()
+        end_ref = torch.get_rng_state()
+        torch.set_rng_state(st)
+        b = fn_new()
+        assert torch.equal(torch.get_rng_state(), end_ref)
+        assert a.shape == b.shape and _rel(b, a) < 1e-5
+    noise = rv(err, mode="test").detach()
+    st = torch.get_rng_state()
+    a = rm(X, noise, mode="test", phase=1).detach()
+    torch.set_rng_state(st)
+    b = m(X, noise, mode="test", phase=1)
+    assert _rel(b, a) < 1e-5

@@ -197,3 +197,33 @@ def test_ref_port(step):
     post = O.params_from_state_dict(m.state_dict(), np.ones((p, p)))
     for k in O.PARAM_KEYS:
         assert _rel(post[k].numpy(), prm[k].numpy()) < 5e-6, k
+
+
+@pytest.fixture(scope="module")
+def ph2():
+    return np.load(os.path.join(GOLDEN, "p10_phase2.npz"))
+
+
+def test_phase2_iteration_matches_reference(ph2):
+    """Pruned CRVAE (golden GC as connection; ragged heads) + VRAE4E + Adam: one full phase-2 iteration."""
+    conn = ph2["connection"]
+    prm = {k: torch.from_numpy(ph2["c_init." + k].copy()) for k in O.PARAM_KEYS}
+    prm["mask"] = torch.from_numpy(ph2["c_init.mask"].copy())
+    assert np.array_equal(prm["mask"].numpy(), O.connection_mask(conn))
+    vprm = {k: torch.from_numpy(ph2["v_init." + k].copy()) for k in O.VRAE_KEYS}
+    wins = O.arrange_input(torch.from_numpy(np.load(os.path.join(GOLDEN, "p10_traj.npz"))["data"].T.copy()), 20)[0]
+    X = wins[ph2["idx"]]
+    state = {}
+    r = O.phase2_iteration(prm, vprm, state, 1, X, torch.from_numpy(ph2["eps_c"]), torch.from_numpy(ph2["eps_e"]), 5e-2)
+    assert abs(float(r["lossd"]["loss"]) - float(ph2["loss"])) < 2e-6 * float(ph2["loss"])
+    assert abs(float(r["lossd"]["kl"]) - float(ph2["kl"])) < 2e-6 * float(ph2["kl"])
+    assert _rel(r["err"].numpy(), ph2["error"]) < 2e-6
+    assert _rel(r["vact"]["pred"].permute(1, 0, 2).numpy(), ph2["pred_e"]) < 5e-6
+    assert abs(float(r["vloss"]["loss"]) - float(ph2["loss_e"])) < 2e-6 * float(ph2["loss_e"])
+    assert abs(float(r["vloss"]["kl"]) - float(ph2["kl_e"])) < 2e-6 * float(ph2["kl_e"])
+    for k in O.VRAE_KEYS:
+        assert _rel(r["vgrads"][k].numpy(), ph2["v_grad." + k]) < 1e-5, k
+        assert _rel(vprm[k].numpy(), ph2["v_post." + k]) < 1e-6, k           # Adam step
+    for k in O.PARAM_KEYS:
+        assert _rel(r["grads"][k].numpy(), ph2["c_grad." + k]) < 1e-5, k
+        assert _rel(prm[k].numpy(), ph2["c_post." + k]) < 1e-6, k

@@ -7,9 +7,9 @@ anonyme-Zheng/VAE-connexe (CRVAE_lorenz96.py), behind the reference's own Python
 shim module vae_connexe_b200.py at the repository root).
 """
 from .functional import arrange_input, prox_update, regularize, restore_parameters, ridge_regularize
-from .modules import CRVAE, GRU
+from .modules import CRVAE, GRU, VRAE4E
 from .sharding import allgather_rows, head_range
-from .train import Phase1Runner, train_phase1
+from .train import Phase1Runner, Phase2Runner, train_phase1, train_phase2
 
-__all__ = ["CRVAE", "GRU", "train_phase1", "Phase1Runner", "prox_update", "regularize", "ridge_regularize",
+__all__ = ["CRVAE", "GRU", "VRAE4E", "train_phase1", "train_phase2", "Phase1Runner", "Phase2Runner", "prox_update", "regularize", "ridge_regularize",
            "restore_parameters", "arrange_input", "head_range", "allgather_rows"]

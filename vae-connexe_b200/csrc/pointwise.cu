@@ -192,6 +192,32 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
     }
 }
 
+// Adam with the step count held in device memory (CUDA-graph friendly): step = *counter + 1; the
+// bias corrections are evaluated in double exactly as torch/optim/adam.py does on the host.
+__global__ void adam_dev_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                                float* __restrict__ v, long long n, double lr, double b1, double b2, float eps,
+                                const int* __restrict__ counter) {
+    __shared__ float s_neg_step, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        const int step = *counter + 1;
+        const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+        s_neg_step = (float)(-(lr / bc1));
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float one_minus_b1 = (float)(1.0 - b1), b2f = (float)b2, one_minus_b2 = (float)(1.0 - b2);
+    const float neg_step_size = s_neg_step, bc2_sqrt = s_bc2_sqrt;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float g = grad[e];
+        float mm = __fadd_rn(m[e], __fmul_rn(one_minus_b1, __fsub_rn(g, m[e])));
+        float vv = __fadd_rn(__fmul_rn(v[e], b2f), __fmul_rn(__fmul_rn(one_minus_b2, g), g));
+        float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), bc2_sqrt), eps);
+        theta[e] = __fadd_rn(theta[e], __fdiv_rn(__fmul_rn(neg_step_size, mm), denom));
+        m[e] = mm; v[e] = vv;
+    }
+}
+__global__ void incr_kernel(int* counter) { *counter += 1; }
+
 __global__ void __launch_bounds__(1024) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
     __shared__ double sh[32];
     double part = 0.0;
@@ -207,6 +233,27 @@ __global__ void __launch_bounds__(256) dot_small_kernel(const float* __restrict_
     for (int e = threadIdx.x; e < n; e += blockDim.x) part += (double)x[e];
     double tot = block_sum(part, sh);
     if (threadIdx.x == 0) out[0] = (float)(tot * (double)scale);
+}
+
+// y = tanh(x)  /  dx = dy * (1 - y^2)      (VRAE4E: z = tanh(linear_hidden(z)), CRVAE_lorenz96.py:164)
+__global__ void tanh_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        y[e] = tanhf(x[e]);
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        dx[e] = dy[e] * (1.f - y[e] * y[e]);
+}
+// out[c][r] = in[r][c]  (small 2-D transpose through shared memory; err [P][T*B] <-> [T*B][P])
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (r0 + i < rows && c < cols) tile[i][threadIdx.x] = in[(long long)(r0 + i) * cols + c];
+    __syncthreads();
+    int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (c0 + i < cols && r < rows) out[(long long)(c0 + i) * rows + r] = tile[threadIdx.x][i];
 }
 
 static inline int grid_for(long long n, int block = 256, int cap = 148 * 8) {
@@ -295,4 +342,37 @@ extern "C" int crvae_dot_small(const float* x, int n, float scale, float* out, v
     CRVAE_REQUIRE(x && out && n >= 0 && n <= (1 << 20), "bad argument");
     dot_small_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, n, scale, out);
     return check_launch("dot_small_kernel");
+}
+
+extern "C" int crvae_tanh_fwd(const float* x, float* y, int64_t n, void* stream) {
+    CRVAE_REQUIRE(x && y && n >= 0, "bad argument");
+    if (n == 0) return 0;
+    tanh_fwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    return check_launch("tanh_fwd_kernel");
+}
+
+extern "C" int crvae_tanh_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+    CRVAE_REQUIRE(dy && y && dx && n >= 0, "bad argument");
+    if (n == 0) return 0;
+    tanh_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n);
+    return check_launch("tanh_bwd_kernel");
+}
+
+extern "C" int crvae_transpose(const float* in, float* out, int rows, int cols, void* stream) {
+    CRVAE_REQUIRE(in && out && rows > 0 && cols > 0, "bad argument");
+    transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, rows, cols);
+    return check_launch("transpose_kernel");
+}
+
+extern "C" int crvae_adam_step_dev(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                   double lr, double beta1, double beta2, double eps, int* step_counter, void* stream) {
+    CRVAE_REQUIRE(theta && grad && exp_avg && exp_avg_sq && step_counter && n >= 0, "bad argument");
+    if (n > 0) {
+        adam_dev_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(theta, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                       (float)eps, step_counter);
+        int rc = check_launch("adam_dev_kernel");
+        if (rc) return rc;
+    }
+    incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter);
+    return check_launch("incr_kernel");
 }

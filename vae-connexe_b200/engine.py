@@ -131,6 +131,7 @@ class CRVAEEngine:
         self.pred = z(max(P, 1), DEC_STEPS, B)
         self.dpred = z(max(P, 1), DEC_STEPS, B)
         self.err = z(max(P, 1), DEC_STEPS, B)
+        self.err_tbp = z(DEC_STEPS, B, self.p)       # residual for all series, time-major (VRAE4E input)
         self.dh0 = z(max(P, 1), B, H)
         self.sse = z(max(P, 1))
         self.enc_gates = z(1, ENC_STEPS, B, G)
@@ -192,6 +193,18 @@ class CRVAEEngine:
             k.proj_fwd_tc(x_hi, x_lo, w_hi, w_lo, b, gates, P, T, self.B, self.p, t_skip)
         else:
             k.proj_fwd(x, w, b, gates, P, T, self.B, self.p, t_skip)
+
+    def residual(self) -> torch.Tensor:
+        """error = X[:,10:,:] - pred for ALL series as [10, B, p] (:599/:639; detached by construction).
+        Needs a preceding forward(want_err=True).  On a head shard the rows are all-gathered."""
+        err = self.err[: self.P]
+        if self.group is not None:
+            from .sharding import allgather_rows
+            world = torch.distributed.get_world_size(self.group)
+            rank = torch.distributed.get_rank(self.group)
+            err = allgather_rows(err.reshape(self.P, -1), self.p, rank, world, self.group)
+        self.k.transpose(err.reshape(self.p, -1), self.err_tbp, self.p, DEC_STEPS * self.B)
+        return self.err_tbp
 
     def forward_staged(self, want_err: bool = False):
         """forward() on the noise previously staged in self.eps_next (CUDA-graph friendly: the

@@ -40,6 +40,10 @@ SIGNATURES = {
     "crvae_gd_step": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_float, _c_void_p]),
     "crvae_gd_prox_gc": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_float, _c_float, _c_int, _c_void_p]),
     "crvae_adam_step": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_double] * 4 + [_c_int, _c_void_p]),
+    "crvae_adam_step_dev": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_double] * 4 + [_c_void_p, _c_void_p]),
+    "crvae_tanh_fwd": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_void_p]),
+    "crvae_tanh_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p]),
+    "crvae_transpose": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "crvae_sumsq": (_c_int, [_c_void_p, _c_i64, _c_void_p, _c_void_p]),
     "crvae_dot_small": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p]),
     "crvae_axpy": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_float, _c_void_p]),
@@ -82,7 +86,7 @@ def ptr(t: Optional[torch.Tensor]):
         raise CrvaeLibraryError("libcrvae_b200 takes CUDA device pointers only (no CPU path exists)")
     if t.data_ptr() % 4:
         raise CrvaeLibraryError("misaligned tensor")
-    if t.dtype not in (torch.float32, torch.uint8):
+    if t.dtype not in (torch.float32, torch.uint8, torch.int32):
         raise CrvaeLibraryError(f"unsupported dtype {t.dtype}")
     if not t.is_contiguous():
         raise CrvaeLibraryError("tensor must be contiguous")
@@ -181,6 +185,19 @@ class Kernels:
     def adam_step(self, theta, grad, m, v, n, lr, b1, b2, eps, step):
         self._ck(self.lib.crvae_adam_step(ptr(theta), ptr(grad), ptr(m), ptr(v), n, lr, b1, b2, eps, step,
                                           stream_ptr()), "crvae_adam_step")
+
+    def adam_step_dev(self, theta, grad, m, v, n, lr, b1, b2, eps, counter):
+        self._ck(self.lib.crvae_adam_step_dev(ptr(theta), ptr(grad), ptr(m), ptr(v), n, lr, b1, b2, eps, ptr(counter),
+                                              stream_ptr()), "crvae_adam_step_dev")
+
+    def tanh_fwd(self, x, y, n):
+        self._ck(self.lib.crvae_tanh_fwd(ptr(x), ptr(y), n, stream_ptr()), "crvae_tanh_fwd")
+
+    def tanh_bwd(self, dy, y, dx, n):
+        self._ck(self.lib.crvae_tanh_bwd(ptr(dy), ptr(y), ptr(dx), n, stream_ptr()), "crvae_tanh_bwd")
+
+    def transpose(self, src, dst, rows, cols):
+        self._ck(self.lib.crvae_transpose(ptr(src), ptr(dst), rows, cols, stream_ptr()), "crvae_transpose")
 
     def sumsq(self, x, n, out):
         self._ck(self.lib.crvae_sumsq(ptr(x), n, ptr(out), stream_ptr()), "crvae_sumsq")

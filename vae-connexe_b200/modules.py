@@ -280,3 +280,112 @@ class CRVAE(nn.Module):
         if threshold:
             return (torch.abs(norms) > 0).int()
         return norms
+
+
+class _VraeTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, owner, eps_dev):
+        eng = owner.engine
+        eng.forward(eps_dev)
+        owner._fwd_serial += 1
+        ctx.owner, ctx.serial, ctx.eps = owner, owner._fwd_serial, eng.eps.clone()
+        ctx.err = eng.enc_in.clone()
+        B = eng.B
+        lat = eng.lat.clone()
+        return eng.pred.clone(), lat[:, _H:].reshape(1, B, _H), lat[:, :_H].reshape(1, B, _H)
+
+    @staticmethod
+    def backward(ctx, dpred, dlog_var, dmu):
+        owner = ctx.owner
+        eng = owner.engine
+        if owner._fwd_serial != ctx.serial:
+            eng.bind_error(ctx.err)
+            eng.forward(ctx.eps)
+            owner._fwd_serial += 1
+        B = eng.B
+        if dpred is not None:
+            eng.dpred.copy_(dpred)
+        else:
+            eng.dpred.zero_()
+        extra = torch.zeros(B, 2 * _H, dtype=torch.float32, device=eng.device)
+        if dmu is not None:
+            extra[:, :_H] = dmu.reshape(B, _H)
+        if dlog_var is not None:
+            extra[:, _H:] = dlog_var.reshape(B, _H)
+        eng.backward(beta_e=0.0, dlat_extra=extra)
+        return None, None, None
+
+
+class VRAE4E(nn.Module):
+    """Mirror of reference class VRAE4E (:123-179), the error-compensation VRAE of phase 2:
+    VRAE4E(num_series, hidden); forward(X, mode) -> (pred, log_var, mu) in train mode (:169)."""
+
+    def __init__(self, num_series, hidden, device: Optional[str] = None, _init: bool = True):
+        super().__init__()
+        _require_hidden(hidden)
+        from .vrae_engine import VRAE4EEngine
+        kern = L.kernels()
+        if device is not None:
+            self.device = torch.device(device)
+        elif kern.device_type == "cuda":
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            self.device = torch.device(kern.device_type)
+        self.p, self.hidden = int(num_series), int(hidden)
+        self.engine = VRAE4EEngine(self.p, self.device)
+        th, g = self.engine.theta, self.engine.grad
+        if _init:
+            # declaration order of the reference (:133-144): gru_left, fc_mu, fc_std, linear_hidden, gru, linear
+            enc = nn.GRU(self.p, _H, batch_first=True)
+            fc_mu, fc_std, hid = nn.Linear(_H, _H), nn.Linear(_H, _H), nn.Linear(_H, _H)
+            dec = nn.GRU(self.p, _H, batch_first=True)
+            out = nn.Linear(_H, self.p)
+            with torch.no_grad():
+                th["enc_w_ih"].copy_(enc.weight_ih_l0); th["enc_w_hh"].copy_(enc.weight_hh_l0)
+                th["enc_b_ih"].copy_(enc.bias_ih_l0); th["enc_b_hh"].copy_(enc.bias_hh_l0)
+                th["lat_w"][:_H].copy_(fc_mu.weight); th["lat_w"][_H:].copy_(fc_std.weight)
+                th["lat_b"][:_H].copy_(fc_mu.bias); th["lat_b"][_H:].copy_(fc_std.bias)
+                th["hid_w"].copy_(hid.weight); th["hid_b"].copy_(hid.bias)
+                th["dec_w_ih"].copy_(dec.weight_ih_l0); th["dec_w_hh"].copy_(dec.weight_hh_l0)
+                th["dec_b_ih"].copy_(dec.bias_ih_l0); th["dec_b_hh"].copy_(dec.bias_hh_l0)
+                th["out_w"].copy_(out.weight); th["out_b"].copy_(out.bias)
+        self.gru_left = _GRUParams(th["enc_w_ih"], th["enc_w_hh"], th["enc_b_ih"], th["enc_b_hh"],
+                                   g["enc_w_ih"], g["enc_w_hh"], g["enc_b_ih"], g["enc_b_hh"])
+        self.fc_mu = _LinearParams(th["lat_w"][:_H], th["lat_b"][:_H], g["lat_w"][:_H], g["lat_b"][:_H])
+        self.fc_std = _LinearParams(th["lat_w"][_H:], th["lat_b"][_H:], g["lat_w"][_H:], g["lat_b"][_H:])
+        self.linear_hidden = _LinearParams(th["hid_w"], th["hid_b"], g["hid_w"], g["hid_b"])
+        self.gru = _GRUParams(th["dec_w_ih"], th["dec_w_hh"], th["dec_b_ih"], th["dec_b_hh"],
+                              g["dec_w_ih"], g["dec_w_hh"], g["dec_b_ih"], g["dec_b_hh"])
+        self.linear = _LinearParams(th["out_w"], th["out_b"], g["out_w"], g["out_b"])
+        self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
+        self._fwd_serial = 0
+        self._pinned = None
+
+    def init_hidden(self, batch):
+        return torch.zeros(1, batch, self.hidden, device=self.device)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.engine.zero_grad()
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def __deepcopy__(self, memo):
+        new = VRAE4E(self.p, self.hidden, device=str(self.device), _init=False)
+        new.engine.theta.flat.copy_(self.engine.theta.flat)
+        new.engine.exp_avg.copy_(self.engine.exp_avg); new.engine.exp_avg_sq.copy_(self.engine.exp_avg_sq)
+        new.engine.adam_counter.copy_(self.engine.adam_counter)
+        return new
+
+    _draw_eps = CRVAE._draw_eps
+
+    def forward(self, X, mode="train"):
+        if mode == "train":
+            self.engine.bind_error(X.transpose(0, 1))          # (B,10,p) -> time-major
+            eps = self._draw_eps(X.shape[0])
+            pred, log_var, mu = _VraeTrainFn.apply(self._anchor, self, eps[0])
+            return pred.permute(1, 0, 2), log_var, mu            # (B,10,p), (1,B,H), (1,B,H)  (:169)
+        if mode == "test":
+            from .generate import vrae_generate
+            return vrae_generate(self, X)
+        raise ValueError(mode)

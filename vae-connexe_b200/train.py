@@ -193,3 +193,147 @@ def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0,
         eng.restore(best_snap)
     crvae.best_it = best_it
     return train_loss_list
+
+
+class Phase2Runner:
+    """CRVAE + VRAE4E on one fixed batch (phase 2, :609-643): [VRAE backward + Adam, CRVAE backward +
+    GD (+prox)] and [CRVAE forward -> residual -> VRAE forward], with optional CUDA-graph replay."""
+
+    def __init__(self, crvae, vrae, Xb, lr, lam, lam_ridge, beta=1.0, beta_e=1.0, use_graphs=True):
+        self.c, self.v = crvae.engine, vrae.engine
+        self.lr, self.lam, self.lam_ridge, self.beta, self.beta_e = lr, lam, lam_ridge, beta, beta_e
+        self.c.bind_batch(Xb)
+        self.use_graphs = use_graphs
+        self.g_full = self.g_update = self.g_fwd = None
+
+    def update(self):
+        self.v.backward(self.beta_e)                  # smooth_e.backward() (:611)
+        if self.lam == 0:
+            self.v.adam_step()                        # optimizer.step(); optimizer.zero_grad() (:612-614)
+        self.c.backward(self.beta, self.lam_ridge)    # smooth.backward() (:616)
+        self.c.step(self.lr, self.lam)                # GD (:617-618) + prox (:621-623)
+
+    def forward_staged(self):
+        self.c.forward_staged(want_err=True)          # :630-637
+        self.v.bind_error(self.c.residual())          # :639
+        self.v.forward_staged()                       # :640-643
+
+    def forward(self, eps_c, eps_e):
+        self.c.eps_next.copy_(eps_c, non_blocking=True)
+        self.v_stage(eps_e)
+        if self.g_fwd is not None:
+            self.g_fwd.replay()
+        else:
+            self.forward_staged()
+
+    def v_stage(self, eps_e):
+        if self.v.B is None:
+            self.v._alloc(self.c.B)
+        self.v.eps_next.copy_(eps_e, non_blocking=True)
+
+    def capture(self):
+        if not self.use_graphs or self.c.device.type != "cuda":
+            self.use_graphs = False
+            return
+        torch.cuda.synchronize()
+        pool, graphs = None, []
+        for body in ((self.update,), (self.forward_staged,), (self.update, self.forward_staged)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                for fn in body:
+                    fn()
+            pool = g.pool()
+            graphs.append(g)
+        self.g_update, self.g_fwd, self.g_full = graphs
+        torch.cuda.synchronize()
+
+    def run_update(self):
+        if self.g_update is not None:
+            self.g_update.replay()
+        else:
+            self.update()
+
+    def iterate(self, eps_c, eps_e):
+        self.c.eps_next.copy_(eps_c, non_blocking=True)
+        self.v.eps_next.copy_(eps_e, non_blocking=True)
+        if self.g_full is not None:
+            self.g_full.replay()
+        else:
+            self.update()
+            self.forward_staged()
+
+
+def train_phase2(crvae, vrae, X, context, lr, max_iter, lam=0, lam_ridge=0,
+                 lookback=5, check_every=50, verbose=1, sparsity=100, batch_size=256,
+                 use_graphs=True, log: Optional[List[dict]] = None):
+    """Phase-2 trainer, same signature as the reference (:562-563).  Keeps: Adam(lr=1e-3) on the VRAE
+    stepped only when lam == 0 (:565, :612-614); GD (+prox) on the CRVAE; beta = beta_e = 1
+    (:582-583); the unused np.random.randint draw of every iteration (:628); noise-draw order
+    (CRVAE :630, VRAE :640; check block: CRVAE :648, VRAE test :173, CRVAE test :266); best CRVAE
+    checkpoint restore (:673-676, :696).  The check block's generated sample is not materialised
+    (the reference only plots / saves it, :685-693) but its noise draws are consumed."""
+    p = X.shape[-1]
+    ce, ve = crvae.engine, vrae.engine
+    train_loss_list = []
+    X_all = torch.cat([arrange_input(x, context)[0] for x in X], dim=0)
+    idx = np.random.randint(len(X_all), size=(batch_size,))                 # :576
+    Xb = X_all[torch.from_numpy(idx).to(X_all.device)]
+    B = Xb.shape[0]
+    best_it, best_loss, best_snap = None, np.inf, None
+    checks = len(range(0, max_iter, check_every)) if max_iter > 0 else 0
+    feed = _NoiseFeed(B, 2 + 2 * max_iter + 3 * checks, ce.device)
+    run = Phase2Runner(crvae, vrae, Xb, lr, lam, lam_ridge, use_graphs=use_graphs)
+    rank0 = getattr(crvae, "rank", 0) == 0
+    world = getattr(crvae, "world_size", 1)
+
+    run.forward(feed.next(), feed.next())                                   # :590-603
+    captured = False
+    for it in range(max_iter):
+        check = it % check_every == 0
+        eps_c, eps_e = feed.next(), feed.next()                             # :630, :640 draws
+        if check:
+            eps_check = feed.next()                                         # :648
+            feed.next(); feed.next()                                        # :679 -> :173 and :681 -> :266 (samples not used)
+        if not check and captured:
+            np.random.randint(len(X_all), size=(batch_size,))               # :628 (result unused, stream advanced)
+            run.iterate(eps_c, eps_e)
+            continue
+        run.run_update()                                                    # :611-625
+        np.random.randint(len(X_all), size=(batch_size,))                   # :628
+        if check:
+            ce.eps_next.copy_(eps_check, non_blocking=True)
+            ce.forward_staged()                                             # :648 (evaluated before :630, same weights)
+            loss_t = ce.loss.clone()
+            ridge_t = ce.ridge_value(lam_ridge)
+            if world > 1:
+                torch.distributed.all_reduce(loss_t, group=crvae.group)
+                if lam_ridge != 0:
+                    ridge_t = ridge_t.clone()
+                    torch.distributed.all_reduce(ridge_t, group=crvae.group)
+        run.forward(eps_c, eps_e)                                           # :630-643
+        if use_graphs and not captured:
+            run.capture()
+            captured = True
+        if not check:
+            continue
+        mean_loss = np.float32(np.float32(float(loss_t) + float(ridge_t)) / np.float32(p))    # :654-659
+        kl_val, kl_e = float(ce.kl), float(ve.kl)
+        smooth_e = float(np.float32(float(ve.loss)) + np.float32(kl_e))
+        usage = float(100 * torch.mean(crvae.GC().float())) if lam > 0 else None
+        if verbose > 0 and rank0:
+            print(('-' * 10 + 'Iter = %d' + '-' * 10) % (it))
+            print('Loss = %f' % mean_loss)
+            print('KL = %f' % kl_val)
+            print('Loss_e = %f' % smooth_e)
+            print('KL_e = %f' % kl_e)
+            if lam > 0:
+                print('Variable usage = %.2f%%' % usage)
+        if log is not None:
+            log.append(dict(it=it, mean_loss=float(mean_loss), kl=kl_val, loss_e=smooth_e, kl_e=kl_e, usage=usage))
+        if mean_loss < best_loss:                                           # :673-676 (CRVAE only)
+            best_loss, best_it = mean_loss, it
+            best_snap = ce.snapshot()
+    if best_snap is not None:                                               # :696
+        ce.restore(best_snap)
+    crvae.best_it = best_it
+    return train_loss_list
