@@ -288,10 +288,13 @@ def run_ours(args):
     e2e = units * args.steps / (ms_e2e * 1e-3)
 
     stages = profile_stages(run, [eps_dev[i] for i in range(n_eps)], reps=max(3, min(args.steps, 20)))
+    # CUDA graphs that captured NCCL kernels must be gone before the communicator is torn down
+    run.g_full = run.g_update = run.g_fwd = None
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        _hard_exit()
     pk = _peaks()
     P_loc, K = eng.P, p_total
     units_loc = B * TD * P_loc
@@ -340,7 +343,14 @@ def run_ours(args):
     }
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        _hard_exit()
+
+
+def _hard_exit():
+    """Multi-rank runs leave through os._exit after flushing: communicator teardown with captured
+    NCCL graphs alive has been seen to hang, and the line is already printed."""
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

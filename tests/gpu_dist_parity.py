@@ -1,0 +1,66 @@
+"""Multi-GPU parity script (run under torchrun on a multi-GPU box, not collected by pytest):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tests/gpu_dist_parity.py
+Head-sharded train_phase1 / train_phase2 over NCCL must reproduce the single-GPU run: identical check
+log, GC equal on every rank, weights within 1e-4."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import vae_connexe_b200 as V  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    traj = np.load(os.path.join(ROOT, "tests", "golden", "p10_traj.npz"))
+    ph2 = np.load(os.path.join(ROOT, "tests", "golden", "p10_phase2.npz"))
+    Xt = torch.from_numpy(traj["data"].T.copy())[None].cuda()
+    ok = True
+
+    def run(sharded, phase):
+        torch.manual_seed(0); np.random.seed(0)
+        kw = dict(rank=rank, world_size=world, group=dist.group.WORLD) if sharded else {}
+        log = []
+        if phase == 1:
+            m = V.CRVAE(10, np.ones((10, 10)), 64, **kw)
+            V.train_phase1(m, Xt, context=20, lam=0.1, lam_ridge=0.01, lr=5e-2, max_iter=61, check_every=20, verbose=0, log=log)
+            return m, None, log
+        m = V.CRVAE(10, ph2["connection"], 64, **kw)
+        v = V.VRAE4E(10, 64)
+        V.train_phase2(m, v, Xt, context=20, lam=0., lam_ridge=0, lr=5e-2, max_iter=21, check_every=10, verbose=0, log=log)
+        return m, v, log
+
+    for phase in (1, 2):
+        ms, vs, logs = run(True, phase)
+        m1, v1, log1 = run(False, phase)          # every rank also runs the unsharded model on its own GPU
+        for a, b in zip(logs, log1):
+            for key in a:
+                if a[key] is not None and abs(a[key] - b[key]) > 1e-4 * abs(b[key]) + 1e-6:
+                    ok = False; print(f"[rank {rank}] phase {phase} log mismatch", key, a, b)
+        if phase == 1 and not torch.equal(ms.GC(), m1.GC()):
+            ok = False; print(f"[rank {rank}] GC mismatch")
+        sd1 = m1.state_dict()
+        for k, t in ms.state_dict().items():
+            rel = float((t - sd1[k]).abs().max() / sd1[k].abs().max().clamp_min(1e-30))
+            if rel > 1e-4:
+                ok = False; print(f"[rank {rank}] phase {phase} weight mismatch {k}: {rel:.2e}")
+        if vs is not None:
+            rel = float((vs.engine.theta.flat - v1.engine.theta.flat).abs().max() / v1.engine.theta.flat.abs().max())
+            if rel > 1e-4:
+                ok = False; print(f"[rank {rank}] VRAE weights mismatch {rel:.2e}")
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_PARITY", "PASS" if flag.item() == 1.0 else "FAIL", f"world={world}")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
