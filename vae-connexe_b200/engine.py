@@ -94,6 +94,8 @@ class CRVAEEngine:
             self.enc_w_hi, self.enc_w_lo = zl(self.theta["enc_w_ih"]), zl(self.theta["enc_w_ih"])
         self.B = None
         self.kl_form = L.KL_SWAPPED
+        self._side = None
+        self.use_side_stream = True
 
     # ------------------------------------------------------------------ batch binding
     def bind_batch(self, X: torch.Tensor):
@@ -153,9 +155,11 @@ class CRVAEEngine:
         k = self.k
         nbytes = max(k.gru_bwd_workspace(max(P, 1), B), k.gru_bwd_workspace(1, B))
         self.ws_gru = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)
+        self.ws_gru_enc = torch.zeros(k.gru_bwd_workspace(1, B) // 4 + 4, dtype=torch.float32, device=dev)
         nbytes = max(k.proj_wgrad_workspace(max(P, 1), DEC_STEPS, B, self.p),
                      k.proj_wgrad_workspace(1, ENC_STEPS, B, self.p))
         self.ws_wgrad = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)
+        self.ws_wgrad_dec = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)   # side-stream twin
 
     # ------------------------------------------------------------------ forward
     def forward(self, eps: Optional[torch.Tensor] = None, want_err: bool = False):
@@ -164,17 +168,24 @@ class CRVAEEngine:
         k, th, B, P, p_ = self.k, self.theta, self.B, self.P, self.p
         if eps is not None:
             self.eps.copy_(eps.reshape(B, H), non_blocking=True)
-        # encoder GRU (gru_left, :208) -> h_T
-        self._project(self.enc_in, "enc", th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, ENC_STEPS, 0)
-        k.gru_fwd(self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
-                  self.enc_hs, self.enc_ghn, None, 1, ENC_STEPS, B, 0)
-        hT = self.enc_hs[0, ENC_STEPS - 1]
-        # [mu | log_var] = h_T [fc_mu ; fc_std]^T + b (:210-211); z = mu + exp(.5 lv) eps (:213-216); KL (:486)
-        k.gemm(L.GEMM_NT, 1, B, 2 * H, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * H, 0, th["lat_b"], 0)
-        k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, self.kl_form)
-        # decoder heads (:218-219 -> GRU.forward :114-121): projection, recurrence (+Linear), MSE
+        # The decoder heads' input projection does not depend on the encoder.  The (latency-bound,
+        # replicated) encoder chain runs on a HIGH-PRIORITY side stream so its few CTAs are scheduled
+        # as soon as an SM frees up, while the big projection GEMM fills the machine from the main stream.
+        side = self._fork()
+        with self._on(side):
+            # encoder GRU (gru_left, :208) -> h_T
+            self._project(self.enc_in, "enc", th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, ENC_STEPS, 0)
+            k.gru_fwd(self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
+                      self.enc_hs, self.enc_ghn, None, 1, ENC_STEPS, B, 0)
+            hT = self.enc_hs[0, ENC_STEPS - 1]
+            # [mu | log_var] = h_T [fc_mu ; fc_std]^T + b (:210-211); z = mu + exp(.5 lv) eps (:213-216); KL (:486)
+            k.gemm(L.GEMM_NT, 1, B, 2 * H, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * H, 0, th["lat_b"], 0)
+            k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, self.kl_form)
         if P > 0:
             self._project(self.dec_in, "dec", th["w_ih"], th["b_ih"], self.gates, P, DEC_STEPS, 1)
+        self._join(side)
+        # decoder heads (:218-219 -> GRU.forward :114-121): recurrence (+Linear), MSE
+        if P > 0:
             k.gru_fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
                       self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
             k.mse_fwd_bwd(self.pred, self.target, self.sse, self.dpred, self.err if want_err else None,
@@ -182,6 +193,28 @@ class CRVAEEngine:
             k.dot_small(self.sse, P, 1.0 / (DEC_STEPS * B), self.loss)
         else:
             self.loss.zero_()
+
+    # ------------------------------------------------------------------ side stream (fork / join; capturable)
+    def _fork(self):
+        if self.device.type != "cuda" or not self.use_side_stream:
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)      # higher than the default stream
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._side.wait_event(ev)
+        return self._side
+
+    def _on(self, side):
+        import contextlib
+        return torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+
+    def _join(self, side):
+        if side is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(side)
+        torch.cuda.current_stream().wait_event(ev)
 
     def _project(self, x, which, w, b, gates, P, T, t_skip):
         """gates = b + x . w^T for all heads / timesteps: tcgen05 3xTF32 GEMM or exact FFMA GEMM."""
@@ -219,32 +252,38 @@ class CRVAEEngine:
         if P > 0:
             k.gru_bwd(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
                       g["w_hh"], g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
+        # The latent / encoder backward chain (small, latency-bound) goes to the high-priority side stream;
+        # the big projection weight-gradient GEMM, which only needs dgates, stays on the main stream.
+        side = self._fork()
+        with self._on(side):
+            # dz = sum over ALL heads of dh0 (every head's h0 is z, :218)
+            if self.group is not None:
+                k.latent_bwd(self.dh0 if P > 0 else None, P, None, None, None, 0.0, self.kl_form, None, self.dz_part, B)
+                torch.distributed.all_reduce(self.dz_part, group=self.group)
+                k.latent_bwd(None, 0, self.dz_part, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+            else:
+                k.latent_bwd(self.dh0, P, None, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+            if dlat_extra is not None:
+                k.axpy(self.dlat, dlat_extra, B * 2 * H, 1.0)
+            hT = self.enc_hs[0, ENC_STEPS - 1]
+            # fc_mu|fc_std: dW = dlat^T hT, db = column sums, dhT = dlat W
+            k.gemm(L.GEMM_TN, 1, 2 * H, H, B, self.dlat, 2 * H, 0, hT, H, 0, g["lat_w"], H, 0)
+            k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
+            k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
+            # encoder BPTT: gradient enters only through h_T
+            k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
+                      None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
+                      1, ENC_STEPS, B, self.ws_gru_enc)
+            k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
+        if P > 0:
             if self.proj_mode == "tc3":
                 k.proj_wgrad_tc(self.gates, self.dec_in_hi, self.dec_in_lo, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1)
             else:
-                k.proj_wgrad(self.gates, self.dec_in, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1, self.ws_wgrad)
+                k.proj_wgrad(self.gates, self.dec_in, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1, self.ws_wgrad_dec)
             if lam_ridge != 0.0:      # d/dW of lam*(|linear.W|^2 + |W_hh|^2), ridge_regularize :321-325
                 k.axpy(g["w_hh"], th["w_hh"], P * G * H, 2.0 * lam_ridge)
                 k.axpy(g["w_lin"], th["w_lin"], P * H, 2.0 * lam_ridge)
-        # dz = sum over ALL heads of dh0 (every head's h0 is z, :218)
-        if self.group is not None:
-            k.latent_bwd(self.dh0 if P > 0 else None, P, None, None, None, 0.0, self.kl_form, None, self.dz_part, B)
-            torch.distributed.all_reduce(self.dz_part, group=self.group)
-            k.latent_bwd(None, 0, self.dz_part, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
-        else:
-            k.latent_bwd(self.dh0, P, None, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
-        if dlat_extra is not None:
-            k.axpy(self.dlat, dlat_extra, B * 2 * H, 1.0)
-        hT = self.enc_hs[0, ENC_STEPS - 1]
-        # fc_mu|fc_std: dW = dlat^T hT, db = column sums, dhT = dlat W
-        k.gemm(L.GEMM_TN, 1, 2 * H, H, B, self.dlat, 2 * H, 0, hT, H, 0, g["lat_w"], H, 0)
-        k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
-        k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
-        # encoder BPTT: gradient enters only through h_T
-        k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
-                  None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
-                  1, ENC_STEPS, B, self.ws_gru)
-        k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
+        self._join(side)
 
     # ------------------------------------------------------------------ update
     def step(self, lr: float, lam: float):
