@@ -117,6 +117,14 @@ int crvae_gru_fwd(float* gates, const float* b_ih, const float* w_hh, const floa
                   float* hs, float* ghn, float* pred,
                   int P, int T, int B, int t_skip, void* stream);
 
+/* Tensor-core form of crvae_gru_fwd (same buffers and results to fp32 rounding): the per-step gate
+ * GEMM h.W_hh^T runs on tcgen05 (3xTF32, accumulator in TMEM), W_hh (hi/lo from crvae_split_tf32,
+ * [P,G,H] each) stays resident in shared memory for all timesteps.                                  */
+int crvae_gru_fwd_tc(float* gates, const float* b_ih, const float* w_hh_hi, const float* w_hh_lo,
+                     const float* b_hh, const float* h0, int64_t h0_head_stride,
+                     const float* w_lin, const float* b_lin, float* hs, float* ghn, float* pred,
+                     int P, int T, int B, int t_skip, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Hand-written BPTT for the above (replaces autograd through :119-:120, triggered at :497).
  * gates [P,T,B,G]  in: r | z | n   out: dgi = [da_r | da_z | da_n]  (in place)

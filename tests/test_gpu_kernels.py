@@ -155,6 +155,31 @@ def test_gru_forward_backward(P, T, B, tile, lin, t_skip, shared_h0):
         k.set_batch_tile(0)
 
 
+@pytest.mark.parametrize("P,T,B,lin,t_skip,shared_h0", [(3, 10, 256, True, 1, True), (2, 10, 100, True, 1, False),
+                                                         (2, 3, 300, False, 0, True), (1, 10, 128, True, 0, False),
+                                                         (20, 10, 256, True, 1, True)])
+def test_gru_forward_tensor_core(P, T, B, lin, t_skip, shared_h0):
+    """tcgen05 recurrent forward (3xTF32 gate GEMM, fast sigmoid/tanh) against the CPU oracle."""
+    k, o = _k(), OracleKernels()
+    gi = _rand(P, T, B, G, seed=1)
+    b_ih, w_hh, b_hh = _rand(P, G, seed=2, scale=0.2), _rand(P, G, H, seed=3, scale=0.125), _rand(P, G, seed=4, scale=0.2)
+    h0 = _rand(B, H, seed=5) if shared_h0 else _rand(P, B, H, seed=5)
+    stride = 0 if shared_h0 else B * H
+    w_lin, b_lin = (_rand(P, H, seed=6, scale=0.2), _rand(P, seed=7)) if lin else (None, None)
+    c = lambda t: None if t is None else t.cuda()
+    ref = dict(g=gi.clone(), hs=torch.zeros(P, T, B, H), ghn=torch.zeros(P, T, B, H), pred=torch.zeros(P, T, B) if lin else None)
+    o.gru_fwd(ref["g"], b_ih, w_hh, b_hh, h0, stride, w_lin, b_lin, ref["hs"], ref["ghn"], ref["pred"], P, T, B, t_skip)
+    out = dict(g=gi.clone().cuda(), hs=torch.zeros(P, T, B, H, device="cuda"), ghn=torch.zeros(P, T, B, H, device="cuda"),
+               pred=torch.zeros(P, T, B, device="cuda") if lin else None)
+    wc = w_hh.cuda()
+    wh, wl = torch.empty_like(wc), torch.empty_like(wc)
+    k.split_tf32(wc, wh, wl, wc.numel())
+    k.gru_fwd_tc(out["g"], c(b_ih), wh, wl, c(b_hh), c(h0), stride, c(w_lin), c(b_lin), out["hs"], out["ghn"], out["pred"], P, T, B, t_skip)
+    torch.cuda.synchronize()
+    for name in ("g", "hs", "ghn") + (("pred",) if lin else ()):
+        assert _rel(out[name], ref[name]) < 2e-5, (name, _rel(out[name], ref[name]))
+
+
 @pytest.mark.parametrize("form", [0, 1])
 @pytest.mark.parametrize("B", [64, 256])
 def test_latent_fwd_bwd(form, B):

@@ -92,6 +92,10 @@ class CRVAEEngine:
             zl = lambda t: torch.zeros_like(t)
             self.w_ih_hi, self.w_ih_lo = zl(self.theta["w_ih"]), zl(self.theta["w_ih"])
             self.enc_w_hi, self.enc_w_lo = zl(self.theta["enc_w_ih"]), zl(self.theta["enc_w_ih"])
+        # recurrence mode: "tc3" = tcgen05 gate GEMM (worth it once there are enough heads to fill the SMs)
+        self.rec_mode = "tc3" if (hasattr(self.k, "gru_fwd_tc") and P >= 8) else "exact"
+        if self.rec_mode == "tc3":
+            self.w_hh_hi, self.w_hh_lo = torch.zeros_like(self.theta["w_hh"]), torch.zeros_like(self.theta["w_hh"])
         self.B = None
         self.kl_form = L.KL_SWAPPED
         self._side = None
@@ -186,8 +190,13 @@ class CRVAEEngine:
         self._join(side)
         # decoder heads (:218-219 -> GRU.forward :114-121): recurrence (+Linear), MSE
         if P > 0:
-            k.gru_fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
-                      self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
+            if self.rec_mode == "tc3":
+                k.split_tf32(th["w_hh"], self.w_hh_hi, self.w_hh_lo, P * G * H)
+                k.gru_fwd_tc(self.gates, th["b_ih"], self.w_hh_hi, self.w_hh_lo, th["b_hh"], self.zlat, 0, th["w_lin"],
+                             th["b_lin"], self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
+            else:
+                k.gru_fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
+                          self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
             k.mse_fwd_bwd(self.pred, self.target, self.sse, self.dpred, self.err if want_err else None,
                           P, DEC_STEPS, B)
             k.dot_small(self.sse, P, 1.0 / (DEC_STEPS * B), self.loss)

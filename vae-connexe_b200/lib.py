@@ -31,6 +31,7 @@ SIGNATURES = {
     "crvae_proj_wgrad_workspace": (_c_size_t, [_c_int] * 4),
     "crvae_proj_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
     "crvae_gru_fwd": (_c_int, [_c_void_p] * 5 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
+    "crvae_gru_fwd_tc": (_c_int, [_c_void_p] * 6 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
     "crvae_gru_bwd_workspace": (_c_size_t, [_c_int] * 2),
     "crvae_gru_bwd": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 11 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
     "crvae_latent_fwd": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_void_p]),
@@ -153,6 +154,11 @@ class Kernels:
         self._ck(self.lib.crvae_gru_fwd(ptr(gates), ptr(b_ih), ptr(w_hh), ptr(b_hh), ptr(h0), h0_stride, ptr(w_lin),
                                         ptr(b_lin), ptr(hs), ptr(ghn), ptr(pred), P, T, B, t_skip, stream_ptr()),
                  "crvae_gru_fwd")
+
+    def gru_fwd_tc(self, gates, b_ih, w_hh_hi, w_hh_lo, b_hh, h0, h0_stride, w_lin, b_lin, hs, ghn, pred, P, T, B, t_skip):
+        self._ck(self.lib.crvae_gru_fwd_tc(ptr(gates), ptr(b_ih), ptr(w_hh_hi), ptr(w_hh_lo), ptr(b_hh), ptr(h0), h0_stride,
+                                           ptr(w_lin), ptr(b_lin), ptr(hs), ptr(ghn), ptr(pred), P, T, B, t_skip,
+                                           stream_ptr()), "crvae_gru_fwd_tc")
 
     def gru_bwd_workspace(self, P, B) -> int:
         return int(self.lib.crvae_gru_bwd_workspace(P, B))
