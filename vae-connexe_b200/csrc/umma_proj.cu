@@ -25,6 +25,8 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;    // 16384
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;    // 24576
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 81920
 constexpr int TC_TMEM_COLS = 256;
+constexpr int EPI_LD = TC_BN + 1;   // padded row of the epilogue transpose slab (floats)
+static_assert(4 * 32 * EPI_LD * 4 <= TC_STAGES * TC_STAGE_BYTES, "epilogue slabs must fit in the pipeline buffers");
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct ProjTcArgs {
@@ -103,23 +105,34 @@ proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         }
     } else {
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int row = m_tile * TC_BM + q * 32 + lane;
-        mbar_wait(tmem_full, 0);
+        mbar_wait(tmem_full, 0);           // all MMAs done: accumulator complete AND the smem stages are idle
         tc_fence_after();
-        float* crow = a.C + static_cast<long long>(head) * a.c_head_stride + static_cast<long long>(row) * TC_BN;
+        // The accumulator arrives lane = row.  Writing rows straight out would make every store touch 32
+        // different lines, so each warp transposes its 32 x 192 slab through the (now idle) pipeline
+        // buffers: lane-per-row scalar stores into a padded tile (conflict-free), then row-by-row
+        // reads with lane = column -> fully coalesced 128-byte global stores with the bias added.
+        float* slab = reinterpret_cast<float*>(smem) + q * (32 * EPI_LD);
         const float* bias = a.bias + static_cast<long long>(head) * TC_BN;
 #pragma unroll 1
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
             float v[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), v);
             tmem_ld_wait();
-            if (row < a.M) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-                    *reinterpret_cast<float4*>(crow + c0 + j) =
-                        make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w);
-                }
+            for (int j = 0; j < 32; ++j) slab[lane * EPI_LD + c0 + j] = v[j];
+        }
+        __syncwarp();
+        float bcol[TC_BN / 32];
+#pragma unroll
+        for (int i = 0; i < TC_BN / 32; ++i) bcol[i] = __ldg(bias + lane + 32 * i);
+        const int row_base = m_tile * TC_BM + q * 32;
+        float* cbase = a.C + static_cast<long long>(head) * a.c_head_stride + static_cast<long long>(row_base) * TC_BN;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            if (row_base + rr < a.M) {
+#pragma unroll
+                for (int i = 0; i < TC_BN / 32; ++i)
+                    cbase[static_cast<long long>(rr) * TC_BN + lane + 32 * i] = slab[rr * EPI_LD + lane + 32 * i] + bcol[i];
             }
         }
         tc_fence_before();

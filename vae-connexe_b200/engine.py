@@ -92,8 +92,11 @@ class CRVAEEngine:
             zl = lambda t: torch.zeros_like(t)
             self.w_ih_hi, self.w_ih_lo = zl(self.theta["w_ih"]), zl(self.theta["w_ih"])
             self.enc_w_hi, self.enc_w_lo = zl(self.theta["enc_w_ih"]), zl(self.theta["enc_w_ih"])
-        # recurrence mode: "tc3" = tcgen05 gate GEMM (worth it once there are enough heads to fill the SMs)
-        self.rec_mode = "tc3" if (hasattr(self.k, "gru_fwd_tc") and P >= 8) else "exact"
+        # recurrence mode: "exact" = persistent fp32 FFMA kernel (default); "tc3" = tcgen05 gate GEMM
+        # (crvae_gru_fwd_tc: parity-green, but with row-major activations its lane-per-row global I/O is
+        # uncoalesced and it is slower than the FFMA kernel -- see profiles/r01_ncu_summary.md; opt-in)
+        import os as _os
+        self.rec_mode = "tc3" if (_os.environ.get("CRVAE_REC_MODE") == "tc3" and hasattr(self.k, "gru_fwd_tc") and P >= 8) else "exact"
         if self.rec_mode == "tc3":
             self.w_hh_hi, self.w_hh_lo = torch.zeros_like(self.theta["w_hh"]), torch.zeros_like(self.theta["w_hh"])
         self.B = None
