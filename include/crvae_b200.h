@@ -200,6 +200,20 @@ int crvae_transpose(const float* in, float* out, int rows, int cols, void* strea
 int crvae_adam_step_dev(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                         double lr, double beta1, double beta2, double eps, int* step_counter, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Cauchy-Schwarz divergence of the Gaussian posterior against a learnable equal-weight GMM prior,
+ * forward + backward (CR-CS-RAE.py:124-163 gaussian_overlap / cs_divergence_gmm; trainer :568-582):
+ *   cs_mean[0] = mean_b clamp(-log mean_k N(mu_q; mu_k, var_q+var_k) + 0.5 log mean_kk' N(mu_k; mu_k', var_k+var_k')
+ *                             + 0.5 log N(mu_q; mu_q, 2 var_q), min=0)     (exp -> mean -> log, as the reference)
+ * lat [B,2H] = [fc_mu out | fc_std out]; with the reference trainer's swapped unpacking (:563, :570-571)
+ * mu_q = lat[:,H:2H] and var_q = exp(lat[:,0:H]).  prior_mu / prior_logvar [K,H], K <= 32.
+ * dlat, dprior_mu, dprior_logvar = gradient of scale_loss*cs_mean (scale_loss = lambda_cs).
+ * ------------------------------------------------------------------------------------------- */
+size_t crvae_cs_div_workspace(int B, int K);
+int crvae_cs_div_fwd_bwd(const float* lat, const float* prior_mu, const float* prior_logvar, int B, int K,
+                         float scale_loss, float* cs_mean, float* dlat, float* dprior_mu, float* dprior_logvar,
+                         void* workspace, void* stream);
+
 /* Ridge penalty pieces (ridge_regularize :321-325): out[0] = sum(x^2) over n elements.          */
 int crvae_sumsq(const float* x, int64_t n, float* out, void* stream);
 /* out[0] = sum_i scale[i] * x[i] for n <= 4096 values (loss = sum_i sse[i]/(T*B) and friends)     */

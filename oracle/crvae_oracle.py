@@ -482,3 +482,41 @@ def phase2_iteration(prm: Params, vprm: Params, adam_state: dict, step: int, X: 
     if lam > 0:
         prm["w_ih"] = prox_update(prm["w_ih"], lam, lr)
     return dict(act=act, lossd=lossd, grads=grads, err=err, vact=vact, vloss=vloss, vgrads=vgrads)
+
+
+# ----------------------------------------------------------------------------------------------
+# CS-RAE variant: Cauchy-Schwarz divergence to a learnable GMM prior  (CR-CS-RAE.py:107-163, :568-582)
+# ----------------------------------------------------------------------------------------------
+def gaussian_overlap(mu1: Tensor, var1: Tensor, mu2: Tensor, var2: Tensor) -> Tensor:
+    """N(mu1 | mu2, var1 + var2) for diagonal covariances, evaluated as exp(log-density) (CR-CS-RAE.py:124-134)."""
+    var_sum = var1 + var2
+    diff = mu1 - mu2
+    D = mu1.size(-1)
+    log_norm = -0.5 * D * math.log(2 * math.pi) - 0.5 * var_sum.log().sum(dim=-1)
+    log_exp = -0.5 * (diff.pow(2) / var_sum).sum(dim=-1)
+    return (log_norm + log_exp).exp()
+
+
+def cs_divergence_gmm(mu_q: Tensor, var_q: Tensor, mu_p: Tensor, var_p: Tensor) -> Tensor:
+    """D_CS(q || p), Gaussian q vs equal-weight GMM p: exp -> mean -> log, clamp(min=0) (CR-CS-RAE.py:137-163)."""
+    D = mu_q.size(-1)
+    term1 = gaussian_overlap(mu_q.unsqueeze(1), var_q.unsqueeze(1), mu_p.unsqueeze(0), var_p.unsqueeze(0)).mean(dim=1)
+    term2 = gaussian_overlap(mu_p.unsqueeze(1), var_p.unsqueeze(1), mu_p.unsqueeze(0), var_p.unsqueeze(0)).mean()
+    term3 = (-0.5 * D * math.log(2 * math.pi) - 0.5 * (2 * var_q).log().sum(dim=-1)).exp()
+    return (-term1.log() + 0.5 * term2.log() + 0.5 * term3.log()).clamp(min=0)
+
+
+def cs_head(lat: Tensor, prior_mu: Tensor, prior_logvar: Tensor, lambda_cs: float):
+    """The trainer's CS term (:568-582) on lat = [fc_mu out | fc_std out] with its swapped unpacking
+    (mu_q = fc_std out, var_q = exp(fc_mu out)).  Returns mean D_CS and the gradients of lambda_cs * mean
+    w.r.t. lat, prior_mu, prior_logvar.  (Gradients through torch autograd of the restated formula: this
+    small head is exactly what the reference differentiates.)"""
+    Hh = lat.shape[1] // 2
+    lat_ = lat.detach().clone().requires_grad_(True)
+    pm = prior_mu.detach().clone().requires_grad_(True)
+    pl = prior_logvar.detach().clone().requires_grad_(True)
+    mu_q, var_q = lat_[:, Hh:], torch.exp(lat_[:, :Hh])
+    cs = cs_divergence_gmm(mu_q, var_q, pm, pl.exp()).mean()
+    (lambda_cs * cs).backward()
+    z = lambda t: torch.zeros_like(t) if t.grad is None else t.grad
+    return cs.detach(), z(lat_), z(pm), z(pl)

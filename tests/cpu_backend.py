@@ -185,6 +185,15 @@ class OracleKernels:
         self.adam_step(theta, grad, m, v, n, lr, b1, b2, eps, int(counter[0]) + 1)
         counter[0] += 1
 
+    def cs_div_workspace(self, B, K):
+        return 16
+
+    def cs_div_fwd_bwd(self, lat, prior_mu, prior_logvar, B, K, scale_loss, cs_mean, dlat, dprior_mu, dprior_logvar, ws):
+        cs, dl, dm, dv = O.cs_head(lat.reshape(B, 2 * H), prior_mu.reshape(K, H), prior_logvar.reshape(K, H), scale_loss)
+        cs_mean[0] = cs
+        dlat.reshape(B, 2 * H).copy_(dl); dprior_mu.reshape(K, H).copy_(dm); dprior_logvar.reshape(K, H).copy_(dv)
+        self.launches += 3
+
     def tanh_fwd(self, x, y, n):
         y.reshape(-1)[:n] = torch.tanh(x.reshape(-1)[:n]); self.launches += 1
 

@@ -296,3 +296,23 @@ def test_sumsq_axpy():
     yg = y.clone().cuda()
     k.axpy(yg, x[:1000].cuda(), 1000, 0.5)
     assert _rel(yg, y + 0.5 * x[:1000]) < 1e-6
+
+
+@pytest.mark.parametrize("B,K", [(48, 10), (256, 10), (7, 1), (33, 32)])
+def test_cs_divergence_fwd_bwd(B, K):
+    """Cauchy-Schwarz divergence head (CR-CS-RAE.py:124-163) forward + backward vs the oracle."""
+    k = _k()
+    lat, pm, pl = _rand(B, 2 * H, seed=1, scale=0.3), _rand(K, H, seed=2, scale=0.3), _rand(K, H, seed=3, scale=0.2)
+    # (D_CS >= 0 by Cauchy-Schwarz: the clamp(min=0) only acts on rounding noise when q == p exactly, where the
+    #  pass/clamp decision is legitimately ambiguous between implementations -- not constructed here)
+    cs_ref, dl_ref, dm_ref, dv_ref = O.cs_head(lat, pm, pl, 0.1)
+    ws = torch.zeros(k.cs_div_workspace(B, K) // 4 + 4, device="cuda")
+    cs, dl = torch.zeros(1, device="cuda"), torch.zeros(B, 2 * H, device="cuda")
+    dm, dv = torch.zeros(K, H, device="cuda"), torch.zeros(K, H, device="cuda")
+    k.cs_div_fwd_bwd(lat.cuda(), pm.cuda(), pl.cuda(), B, K, 0.1, cs, dl, dm, dv, ws)
+    torch.cuda.synchronize()
+    assert abs(float(cs) - float(cs_ref)) < 2e-5 * max(1.0, abs(float(cs_ref)))
+    scale = float(dl_ref.abs().max())
+    assert float((dl.cpu() - dl_ref).abs().max()) < 1e-4 * scale
+    assert float((dm.cpu() - dm_ref).abs().max()) < 1e-4 * float(dm_ref.abs().max())
+    assert float((dv.cpu() - dv_ref).abs().max()) < 1e-4 * float(dv_ref.abs().max())

@@ -381,3 +381,25 @@ def test_generation_gpu_matches_checker_backend():
     b0, b1 = m(X.cuda(), mode="test"), v(err.cuda(), mode="test")
     b2 = m(X.cuda(), a1[:, 1:].cuda(), mode="test", phase=1)
     assert _rel(b0, a0) < TOL and _rel(b1, a1) < TOL and _rel(b2, a2) < TOL
+
+
+def test_cs_rae_trainer_tracks_golden_log(traj):
+    """Config 5 (CR-CS-RAE.py): CS-divergence trainer on the GPU against the reference's own 11-iteration run."""
+    from vae_connexe_b200 import cs as CS
+    g = np.load(os.path.join(GOLDEN, "cs_p10.npz"))
+    Xt = torch.from_numpy(traj["data"].T.copy())[None].cuda()
+    torch.manual_seed(0); np.random.seed(0)
+    m = CS.CRVAE(10, np.ones((10, 10)), 64, 10, 0.1)
+    log = []
+    CS.train_phase1(m, Xt, context=20, lam=0.5, lam_ridge=0.01, lr=5e-2, max_iter=11, check_every=5, batch_size=128,
+                    lambda_cs=0.1, verbose=0, log=log)
+    assert [r["it"] for r in log] == list(g["log_it"])
+    for i, r in enumerate(log):
+        assert abs(r["mean_loss"] - g["log_mean"][i]) < TOL * g["log_mean"][i] + 2e-6
+        assert abs(r["recon"] - g["log_recon"][i]) < TOL * g["log_recon"][i] + 2e-6
+        assert abs(r["cs"] - g["log_cs"][i]) < TOL * g["log_cs"][i] + 2e-6
+        assert r["usage"] == g["log_usage"][i]
+    post = _engine_tensors(m.engine.theta)
+    for k in O.PARAM_KEYS:
+        assert _rel(post[k], g["final." + k]) < TOL, k
+    assert _rel(m.prior.mu.detach(), g["final.prior_mu"]) < TOL and _rel(m.prior.logvar.detach(), g["final.prior_logvar"]) < TOL

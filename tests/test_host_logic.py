@@ -269,3 +269,29 @@ def test_generation_matches_live_reference(cpu_backend):
     torch.set_rng_state(st)
     b = m(X, noise, mode="test", phase=1)
     assert _rel(b, a) < 1e-5
+
+
+def test_cs_rae_trainer_tracks_reference_log(cpu_backend, traj):
+    """CR-CS-RAE variant (config 5): init order incl. the GMM prior, per-iteration batch resampling, GD on the
+    prior, evaluation on all windows -- against the reference's 11-iteration run (tests/golden/cs_p10.npz)."""
+    from vae_connexe_b200 import cs as CS
+    g = np.load(os.path.join(GOLDEN, "cs_p10.npz"))
+    Xt = torch.from_numpy(traj["data"].T.copy())[None]
+    torch.manual_seed(0); np.random.seed(0)
+    m = CS.CRVAE(10, np.ones((10, 10)), 64, 10, 0.1)
+    prm = O.params_from_state_dict(m.state_dict(), np.ones((10, 10)))
+    for k in O.PARAM_KEYS:
+        assert np.array_equal(prm[k].numpy(), g["init." + k]), k
+    assert np.array_equal(m.prior.mu.detach().numpy(), g["init.prior_mu"])
+    log = []
+    CS.train_phase1(m, Xt, context=20, lam=0.5, lam_ridge=0.01, lr=5e-2, max_iter=11, check_every=5, batch_size=128,
+                    lambda_cs=0.1, verbose=0, log=log)
+    assert [r["it"] for r in log] == list(g["log_it"])
+    for i, r in enumerate(log):
+        assert abs(r["mean_loss"] - g["log_mean"][i]) < 3e-6 and abs(r["recon"] - g["log_recon"][i]) < 3e-6
+        assert abs(r["cs"] - g["log_cs"][i]) < 3e-6 and r["usage"] == g["log_usage"][i]
+    prm = O.params_from_state_dict(m.state_dict(), np.ones((10, 10)))
+    for k in O.PARAM_KEYS:
+        assert _rel(prm[k], g["final." + k]) < 1e-5, k
+    assert _rel(m.prior.mu.detach(), g["final.prior_mu"]) < 1e-5 and _rel(m.prior.logvar.detach(), g["final.prior_logvar"]) < 1e-5
+    assert np.array_equal(torch.get_rng_state().numpy(), g["rng_after"])

@@ -227,3 +227,15 @@ def test_phase2_iteration_matches_reference(ph2):
     for k in O.PARAM_KEYS:
         assert _rel(r["grads"][k].numpy(), ph2["c_grad." + k]) < 1e-5, k
         assert _rel(prm[k].numpy(), ph2["c_post." + k]) < 1e-6, k
+
+
+def test_cs_divergence_matches_reference():
+    """Oracle restatement of gaussian_overlap / cs_divergence_gmm (CR-CS-RAE.py:124-163) and the gradients of
+    the trainer's lambda_cs * mean(D_CS) against the reference's own evaluation (tests/golden/cs_p10.npz)."""
+    g = np.load(os.path.join(GOLDEN, "cs_p10.npz"))
+    lat, pm, pl = (torch.from_numpy(g[k].copy()) for k in ("cs_lat", "cs_pm", "cs_pl"))
+    vals = O.cs_divergence_gmm(lat[:, 64:], torch.exp(lat[:, :64]), pm, pl.exp())
+    assert np.array_equal(vals.numpy(), g["cs_vals"])
+    cs, dl, dm, dv = O.cs_head(lat, pm, pl, 0.1)
+    assert abs(float(cs) - float(g["cs_vals"].mean())) < 1e-6
+    assert np.array_equal(dl.numpy(), g["cs_dlat"]) and np.array_equal(dm.numpy(), g["cs_dpm"]) and np.array_equal(dv.numpy(), g["cs_dpl"])

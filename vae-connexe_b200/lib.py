@@ -42,6 +42,8 @@ SIGNATURES = {
     "crvae_gd_prox_gc": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_float, _c_float, _c_int, _c_void_p]),
     "crvae_adam_step": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_double] * 4 + [_c_int, _c_void_p]),
     "crvae_adam_step_dev": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_double] * 4 + [_c_void_p, _c_void_p]),
+    "crvae_cs_div_workspace": (_c_size_t, [_c_int, _c_int]),
+    "crvae_cs_div_fwd_bwd": (_c_int, [_c_void_p] * 3 + [_c_int, _c_int, _c_float] + [_c_void_p] * 6),
     "crvae_tanh_fwd": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_void_p]),
     "crvae_tanh_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p]),
     "crvae_transpose": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
@@ -195,6 +197,14 @@ class Kernels:
     def adam_step_dev(self, theta, grad, m, v, n, lr, b1, b2, eps, counter):
         self._ck(self.lib.crvae_adam_step_dev(ptr(theta), ptr(grad), ptr(m), ptr(v), n, lr, b1, b2, eps, ptr(counter),
                                               stream_ptr()), "crvae_adam_step_dev")
+
+    def cs_div_workspace(self, B, K) -> int:
+        return int(self.lib.crvae_cs_div_workspace(B, K))
+
+    def cs_div_fwd_bwd(self, lat, prior_mu, prior_logvar, B, K, scale_loss, cs_mean, dlat, dprior_mu, dprior_logvar, ws):
+        self._ck(self.lib.crvae_cs_div_fwd_bwd(ptr(lat), ptr(prior_mu), ptr(prior_logvar), B, K, float(scale_loss), ptr(cs_mean),
+                                               ptr(dlat), ptr(dprior_mu), ptr(dprior_logvar), ptr(ws), stream_ptr()),
+                 "crvae_cs_div_fwd_bwd")
 
     def tanh_fwd(self, x, y, n):
         self._ck(self.lib.crvae_tanh_fwd(ptr(x), ptr(y), n, stream_ptr()), "crvae_tanh_fwd")

@@ -158,6 +158,7 @@ class CRVAE(nn.Module):
         th = eng.theta
         enc = nn.GRU(self.p, _H, batch_first=True)                        # :192
         fc_mu, fc_std = nn.Linear(_H, _H), nn.Linear(_H, _H)              # :195-196
+        self._init_extra()        # hook: variants that declare more parameters before the heads (CR-CS-RAE's prior)
         with torch.no_grad():
             th["enc_w_ih"].copy_(enc.weight_ih_l0); th["enc_w_hh"].copy_(enc.weight_hh_l0)
             th["enc_b_ih"].copy_(enc.bias_ih_l0); th["enc_b_hh"].copy_(enc.bias_hh_l0)
@@ -179,6 +180,9 @@ class CRVAE(nn.Module):
             for name, val in (("w_ih", w_ih), ("w_hh", w_hh), ("b_ih", b_ih), ("b_hh", b_hh), ("w_lin", w_lin),
                               ("b_lin", b_lin)):
                 th[name].copy_(val)
+
+    def _init_extra(self):
+        return None
 
     def state_dict(self, *args, **kwargs):
         """Reference-shaped state_dict (keys of SURVEY 8(a3); pruned heads packed to (3H, k_i));
