@@ -143,12 +143,13 @@ int crvae_gru_bwd(float* gates, const float* ghn, const float* hs,
 
 /* ---------------------------------------------------------------------------------------------
  * Fused reparameterisation + KL  (CRVAE.forward :210-216, VRAE4E.forward :157-163, trainer :486)
- *   lat [B,2H] = [mu | log_var] (output of the fc_mu|fc_std GEMM);  eps [B,H] ~ N(0,1)
- *   z [B,H] = mu + exp(0.5*log_var)*eps
+ *   lat [B,2Z] = [mu | log_var] (output of the fc_mu|fc_std GEMM);  eps [B,Z] ~ N(0,1)
+ *   (Z = latent width: H for CRVAE / VRAE4E, free for the generic VRAE of VRAE.py:105-147)
+ *   z [B,Z] = mu + exp(0.5*log_var)*eps
  *   kl_out[0] = mean_b sum_h KL-term (form: CRVAE_KL_*)                 (single deterministic sum)
  * ------------------------------------------------------------------------------------------- */
 int crvae_latent_fwd(const float* lat, const float* eps, float* z, float* kl_out,
-                     int B, int kl_form, void* stream);
+                     int B, int Z, int kl_form, void* stream);
 
 /* Backward of the above + the sum over heads of dh0 (every head's h0 is z, :218):
  *   dz[b][h] = sum_{i<P} dh0[i][b][h]  (+ dz_extra[b][h] if not NULL; a peer-reduced partial)
@@ -156,17 +157,18 @@ int crvae_latent_fwd(const float* lat, const float* eps, float* z, float* kl_out
  * dh0 may be NULL with P = 0 (then dz = dz_extra).  dz_out (NULL ok) receives the head sum.     */
 int crvae_latent_bwd(const float* dh0, int P, const float* dz_extra, const float* lat,
                      const float* eps, float beta, int kl_form, float* dlat, float* dz_out,
-                     int B, void* stream);
+                     int B, int Z, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused MSE loss forward + backward for all heads (trainer :484, :509; nn.MSELoss 'mean'):
  *   sse[i]         = sum_{t,b} (pred[i][t][b] - target[i][t][b])^2     (loss = sum_i sse[i]/(T*B))
- *   dpred[i][t][b] = 2*(pred - target)/(T*B)
+ *   dpred[i][t][b] = dscale*(pred - target), dscale <= 0 meaning 2/(T*B) (nn.MSELoss 'mean'); VRAE.py's
+ *                    sum-reduced loss / batch (VRAE.py:143) passes dscale = 2/batch
  *   err[i][t][b]   = target - pred          (NULL ok; the phase-2 residual, :599/:639)
  * pred, target, dpred, err [P,T,B]; target is X[:, 10:, i] of the fixed batch, head-major.
  * ------------------------------------------------------------------------------------------- */
 int crvae_mse_fwd_bwd(const float* pred, const float* target, float* sse, float* dpred, float* err,
-                      int P, int T, int B, void* stream);
+                      int P, int T, int B, float dscale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Plain gradient step  theta <- theta - lr*grad  (:498-499), product rounded to fp32 first as
@@ -192,6 +194,10 @@ int crvae_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_
 /* y = tanh(x) and its backward dx = dy*(1-y^2): VRAE4E's z = tanh(linear_hidden(z)) (:164)         */
 int crvae_tanh_fwd(const float* x, float* y, int64_t n, void* stream);
 int crvae_tanh_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+/* Output activation of the generic VRAE decoder (VRAE.py:60-68) and its backward dx = dy * act'(y);
+ * kind: 0 tanh, 1 sigmoid, 2 relu, 3 identity.                                                       */
+int crvae_act_fwd(const float* x, float* y, int64_t n, int kind, void* stream);
+int crvae_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int kind, void* stream);
 /* out[c][r] = in[r][c]: residual [P][T*B] (head-major) <-> [T*B][P] (VRAE4E input, :599/:639)       */
 int crvae_transpose(const float* in, float* out, int rows, int cols, void* stream);
 

@@ -520,3 +520,98 @@ def cs_head(lat: Tensor, prior_mu: Tensor, prior_logvar: Tensor, lambda_cs: floa
     (lambda_cs * cs).backward()
     z = lambda t: torch.zeros_like(t) if t.grad is None else t.grad
     return cs.detach(), z(lat_), z(pm), z(pl)
+
+
+# ----------------------------------------------------------------------------------------------
+# Generic VRAE of VRAE.py (config 4): Encoder :11-36, Decoder :38-102 (GRU variant, teacher forcing 1.0),
+# VRAE.loss :142-147.  Parameters: enc_w_ih [G,D] enc_w_hh [G,H] enc_b_ih enc_b_hh [G] (encoder.rnn),
+# mu_w [Z,H] mu_b [Z] lv_w [Z,H] lv_b [Z] (fc_mu / fc_logvar), z2h_w [H,Z] z2h_b [H] (fc_z2h),
+# dec_w_ih [G,D] dec_w_hh [G,H] dec_b_ih dec_b_hh [G] (decoder.cell, an nn.GRUCell), out_w [D,H] out_b [D] (fc_out)
+# ----------------------------------------------------------------------------------------------
+GVRAE_KEYS = ("enc_w_ih", "enc_w_hh", "enc_b_ih", "enc_b_hh", "mu_w", "mu_b", "lv_w", "lv_b", "z2h_w", "z2h_b",
+              "dec_w_ih", "dec_w_hh", "dec_b_ih", "dec_b_hh", "out_w", "out_b")
+_GVRAE_SD = ("encoder.rnn.weight_ih_l0", "encoder.rnn.weight_hh_l0", "encoder.rnn.bias_ih_l0", "encoder.rnn.bias_hh_l0",
+             "encoder.fc_mu.weight", "encoder.fc_mu.bias", "encoder.fc_logvar.weight", "encoder.fc_logvar.bias",
+             "decoder.fc_z2h.weight", "decoder.fc_z2h.bias", "decoder.cell.weight_ih", "decoder.cell.weight_hh",
+             "decoder.cell.bias_ih", "decoder.cell.bias_hh", "decoder.fc_out.weight", "decoder.fc_out.bias")
+
+
+def gvrae_params_from_state_dict(sd: Dict[str, Tensor], dtype=torch.float32) -> Params:
+    return {k: sd[s].detach().to(dtype).clone().contiguous() for k, s in zip(GVRAE_KEYS, _GVRAE_SD)}
+
+
+def _act(x: Tensor, kind: str) -> Tensor:
+    return {"sigmoid": torch.sigmoid, "tanh": torch.tanh, "relu": torch.relu}.get(kind, lambda t: t)(x)
+
+
+def _act_grad(y: Tensor, kind: str) -> Tensor:
+    if kind == "sigmoid":
+        return y * (1 - y)
+    if kind == "tanh":
+        return 1 - y * y
+    if kind == "relu":
+        return (y > 0).to(y.dtype)
+    return torch.ones_like(y)
+
+
+def gvrae_forward(prm: Params, x: Tensor, eps: Tensor, act: str = "tanh") -> Dict[str, Tensor]:
+    """x (B,T,D); eps (B,Z) the randn_like draw of VRAE.reparameterize (:117-121).  Teacher forcing 1.0:
+    the decoder cell's input at step t is x[:, t] (:82-97)."""
+    dt = prm["enc_w_hh"].dtype
+    x = x.to(dt)
+    B, T, D = x.shape
+    Hh = prm["enc_w_hh"].shape[1]
+    xin = x.transpose(0, 1).contiguous()                                                   # [T,B,D]
+    gi_e = (xin @ prm["enc_w_ih"].t() + prm["enc_b_ih"]).unsqueeze(0)
+    ehs, er, ez, en, eghn = gru_forward(gi_e, torch.zeros(B, Hh, dtype=dt), prm["enc_w_hh"][None], prm["enc_b_hh"][None])
+    hT = ehs[0, -1]
+    mu = hT @ prm["mu_w"].t() + prm["mu_b"]
+    logvar = hT @ prm["lv_w"].t() + prm["lv_b"]
+    std = torch.exp(0.5 * logvar)
+    z = mu + eps.to(dt) * std
+    h0 = torch.tanh(z @ prm["z2h_w"].t() + prm["z2h_b"])                                   # :72
+    gi_d = (xin @ prm["dec_w_ih"].t() + prm["dec_b_ih"]).unsqueeze(0)
+    dhs, dr, dz, dn, dghn = gru_forward(gi_d, h0, prm["dec_w_hh"][None], prm["dec_b_hh"][None])
+    recon = _act(dhs[0, 1:] @ prm["out_w"].t() + prm["out_b"], act)                        # [T,B,D]  (:91)
+    return dict(xin=xin, eps=eps.to(dt), ehs=ehs, er=er, ez=ez, en=en, eghn=eghn, hT=hT, mu=mu, logvar=logvar, std=std, z=z,
+                h0=h0, dhs=dhs, dr=dr, dz=dz, dn=dn, dghn=dghn, recon=recon)
+
+
+def gvrae_loss(a: Dict[str, Tensor], beta: float = 1.0):
+    """VRAE.loss (:142-147): SSE / batch + beta * KLD / batch (standard KL, no name swap here)."""
+    B = a["mu"].shape[0]
+    diff = a["recon"] - a["xin"]
+    rec = (diff * diff).sum() / B
+    kld = -0.5 * torch.sum(1 + a["logvar"] - a["mu"].pow(2) - a["logvar"].exp()) / B
+    return dict(total=rec + beta * kld, rec=rec, kld=kld, diff=diff)
+
+
+def gvrae_backward(prm: Params, a: Dict[str, Tensor], l: Dict[str, Tensor], beta: float = 1.0, act: str = "tanh") -> Params:
+    B = a["mu"].shape[0]
+    drecon = 2.0 * l["diff"] / B
+    dpre = drecon * _act_grad(a["recon"], act)
+    g: Params = {}
+    hs_out = a["dhs"][0, 1:]
+    g["out_w"] = torch.einsum("tbd,tbh->dh", dpre, hs_out)
+    g["out_b"] = dpre.sum((0, 1))
+    dh_out = (dpre @ prm["out_w"])[None]
+    dgi_d, dw, db, dh0 = gru_backward(dh_out, a["dhs"], a["dr"], a["dz"], a["dn"], a["dghn"], prm["dec_w_hh"][None])
+    g["dec_w_ih"] = torch.einsum("tbg,tbk->gk", dgi_d[0], a["xin"])
+    g["dec_b_ih"] = dgi_d[0].sum((0, 1))
+    g["dec_w_hh"], g["dec_b_hh"] = dw[0], db[0]
+    dpre0 = dh0[0] * (1 - a["h0"] * a["h0"])
+    g["z2h_w"] = dpre0.t() @ a["z"]
+    g["z2h_b"] = dpre0.sum(0)
+    dzl = dpre0 @ prm["z2h_w"]
+    dmu = dzl + beta * a["mu"] / B
+    dlv = dzl * a["eps"] * 0.5 * a["std"] + beta * (-0.5 * (1 - torch.exp(a["logvar"]))) / B
+    g["mu_w"] = dmu.t() @ a["hT"]; g["mu_b"] = dmu.sum(0)
+    g["lv_w"] = dlv.t() @ a["hT"]; g["lv_b"] = dlv.sum(0)
+    dhT = dmu @ prm["mu_w"] + dlv @ prm["lv_w"]
+    T = a["er"].shape[1]
+    zero = torch.zeros(1, T, B, dhT.shape[-1], dtype=dhT.dtype)
+    dgi_e, dw, db, _ = gru_backward(zero, a["ehs"], a["er"], a["ez"], a["en"], a["eghn"], prm["enc_w_hh"][None], dh_last=dhT[None])
+    g["enc_w_ih"] = torch.einsum("tbg,tbk->gk", dgi_e[0], a["xin"])
+    g["enc_b_ih"] = dgi_e[0].sum((0, 1))
+    g["enc_w_hh"], g["enc_b_hh"] = dw[0], db[0]
+    return g

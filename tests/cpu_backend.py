@@ -118,13 +118,15 @@ class OracleKernels:
             return 1 + mu - lv * lv - torch.exp(mu)
         return 1 + lv - mu * mu - torch.exp(lv)
 
-    def latent_fwd(self, lat, eps, z, kl_out, B, kl_form):
+    def latent_fwd(self, lat, eps, z, kl_out, B, kl_form, Z=64):
+        H = Z
         mu, lv = lat[:, :H], lat[:, H:]
         z.copy_(mu + torch.exp(0.5 * lv) * eps.reshape(B, H))
         kl_out[0] = (-0.5 * self._kl_terms(mu, lv, kl_form)).sum(-1).mean(0)
         self.launches += 1
 
-    def latent_bwd(self, dh0, P, dz_extra, lat, eps, beta, kl_form, dlat, dz_out, B):
+    def latent_bwd(self, dh0, P, dz_extra, lat, eps, beta, kl_form, dlat, dz_out, B, Z=64):
+        H = Z
         dz = torch.zeros(B, H)
         if P > 0:
             dz = dh0.reshape(-1)[: P * B * H].view(P, B, H).sum(0)
@@ -143,12 +145,12 @@ class OracleKernels:
         dlat[:, :H] = dz + beta * dkm
         dlat[:, H:] = dz * eps.reshape(B, H) * 0.5 * torch.exp(0.5 * lv) + beta * dkl
 
-    def mse_fwd_bwd(self, pred, target, sse, dpred, err, P, T, B):
+    def mse_fwd_bwd(self, pred, target, sse, dpred, err, P, T, B, dscale=0.0):
         pr = pred.reshape(-1)[: P * T * B].view(P, T, B); tg = target.reshape(P, T, B)
         d = pr - tg
         sse.reshape(-1)[:P] = (d * d).sum((1, 2))
         if dpred is not None:
-            dpred.reshape(-1)[: P * T * B].view(P, T, B).copy_(2.0 * d / (T * B))
+            dpred.reshape(-1)[: P * T * B].view(P, T, B).copy_((dscale if dscale > 0 else 2.0 / (T * B)) * d)
         if err is not None:
             err.reshape(-1)[: P * T * B].view(P, T, B).copy_(tg - pr)
         self.launches += 1
@@ -199,6 +201,15 @@ class OracleKernels:
 
     def tanh_bwd(self, dy, y, dx, n):
         dx.reshape(-1)[:n] = dy.reshape(-1)[:n] * (1 - y.reshape(-1)[:n] ** 2); self.launches += 1
+
+    def act_fwd(self, x, y, n, kind):
+        v = x.reshape(-1)[:n]
+        y.reshape(-1)[:n] = [torch.tanh, torch.sigmoid, torch.relu, lambda t: t][kind](v); self.launches += 1
+
+    def act_bwd(self, dy, y, dx, n, kind):
+        v = y.reshape(-1)[:n]
+        gy = [1 - v * v, v * (1 - v), (v > 0).float(), torch.ones_like(v)][kind]
+        dx.reshape(-1)[:n] = dy.reshape(-1)[:n] * gy; self.launches += 1
 
     def transpose(self, src, dst, rows, cols):
         dst.reshape(-1)[: rows * cols].view(cols, rows).copy_(src.reshape(-1)[: rows * cols].view(rows, cols).t())

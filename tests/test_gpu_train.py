@@ -403,3 +403,74 @@ def test_cs_rae_trainer_tracks_golden_log(traj):
     for k in O.PARAM_KEYS:
         assert _rel(post[k], g["final." + k]) < TOL, k
     assert _rel(m.prior.mu.detach(), g["final.prior_mu"]) < TOL and _rel(m.prior.logvar.detach(), g["final.prior_logvar"]) < TOL
+
+
+def test_generic_vrae_matches_reference_golden():
+    """Config 4 (VRAE.py, GRU, teacher forcing 1.0) on the GPU: forward, gradients and an 11-epoch Adam run against the
+    reference's own numbers (tests/golden/vrae_generic.npz)."""
+    from vae_connexe_b200 import vrae as VR
+    g = np.load(os.path.join(GOLDEN, "vrae_generic.npz"))
+    torch.manual_seed(0)
+    data = torch.randn(48, 12, 10)
+    model = VR.VRAE(10, 64, 32, "gru", "tanh")
+    recon, mu, logvar = model(data.cuda())
+    assert _rel(recon, g["recon"]) < TOL and _rel(mu, g["mu"]) < TOL and _rel(logvar, g["logvar"]) < TOL
+    model.engine.backward(0.5)
+    gr = model.engine.grad
+    for name, gold in (("enc_w_ih", "enc_w_ih"), ("enc_w_hh", "enc_w_hh"), ("enc_b_ih", "enc_b_ih"), ("enc_b_hh", "enc_b_hh"),
+                       ("z2h_w", "z2h_w"), ("z2h_b", "z2h_b"), ("dec_w_ih", "dec_w_ih"), ("dec_w_hh", "dec_w_hh"),
+                       ("dec_b_ih", "dec_b_ih"), ("dec_b_hh", "dec_b_hh"), ("out_w", "out_w"), ("out_b", "out_b")):
+        assert _rel(gr[name], g["grad." + gold]) < TOL, name
+    assert _rel(gr["lat_w"][:32], g["grad.mu_w"]) < TOL and _rel(gr["lat_w"][32:], g["grad.lv_w"]) < TOL
+    torch.manual_seed(0)
+    data = torch.randn(48, 12, 10)
+    model = VR.VRAE(10, 64, 32, "gru", "tanh")
+    log = []
+    VR.train(model, data.cuda(), epochs=11, lr=1e-3, beta=0.5, log=log)
+    for i, r in enumerate(log):
+        assert abs(r["total"] - g["log_total"][i]) < 1e-3 and abs(r["kld"] - g["log_kld"][i]) < 1e-3      # 4 printed decimals
+    prm = O.gvrae_params_from_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    for k in O.GVRAE_KEYS:
+        assert _rel(prm[k], g["final." + k]) < 5 * TOL, k
+    assert np.array_equal(torch.get_rng_state().numpy(), g["rng_after"])
+
+
+def test_generic_vrae_config4_shape_against_oracle():
+    """BASELINE config 4 shape family (batch 1024, latent 32, D = 10; seq shortened to 64 for the CPU oracle):
+    one forward/backward against the oracle."""
+    from vae_connexe_b200 import vrae as VR
+    torch.manual_seed(4)
+    B, T, D, Z = 1024, 64, 10, 32
+    model = VR.VRAE(D, 64, Z, "gru", "tanh")
+    prm = O.gvrae_params_from_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    data = torch.randn(B, T, D)
+    st = torch.get_rng_state()
+    eps = torch.randn(B, Z)
+    torch.set_rng_state(st)
+    recon, mu, logvar = model(data.cuda())
+    a = O.gvrae_forward(prm, data, eps, "tanh")
+    l = O.gvrae_loss(a, 1.0)
+    assert _rel(recon.permute(1, 0, 2), a["recon"]) < TOL
+    assert abs(float(model.engine.sse) / B - float(l["rec"])) < TOL * float(l["rec"])
+    assert abs(float(model.engine.kl) - float(l["kld"])) < TOL * float(l["kld"])
+    model.engine.backward(1.0)
+    gr = O.gvrae_backward(prm, a, l, 1.0, "tanh")
+    eg = model.engine.grad
+    for k in ("enc_w_ih", "enc_w_hh", "dec_w_ih", "dec_w_hh", "dec_b_hh", "z2h_w", "out_w", "out_b"):
+        assert _rel(eg[k], gr[k]) < TOL, k
+
+
+def test_generic_vrae_full_config4_runs():
+    """Full BASELINE config 4 size (batch 1024, seq 512, latent 32): two Adam epochs, finite and decreasing loss,
+    deterministic re-run (size-independent properties)."""
+    from vae_connexe_b200 import vrae as VR
+    res = []
+    for rep in range(2):
+        torch.manual_seed(0)
+        data = torch.randn(1024, 512, 10).cuda()
+        model = VR.VRAE(10, 64, 32, "gru", "tanh")
+        log = []
+        VR.train(model, data, epochs=11, lr=1e-3, beta=1.0, log=log)
+        res.append([r["total"] for r in log] + [float(model.engine.theta.flat.double().sum())])
+    assert res[0] == res[1]
+    assert np.isfinite(res[0]).all() and res[0][1] < res[0][0]

@@ -295,3 +295,45 @@ def test_cs_rae_trainer_tracks_reference_log(cpu_backend, traj):
         assert _rel(prm[k], g["final." + k]) < 1e-5, k
     assert _rel(m.prior.mu.detach(), g["final.prior_mu"]) < 1e-5 and _rel(m.prior.logvar.detach(), g["final.prior_logvar"]) < 1e-5
     assert np.array_equal(torch.get_rng_state().numpy(), g["rng_after"])
+
+
+def test_generic_vrae_tracks_reference(cpu_backend):
+    """Config 4 (VRAE.py): init order, forward return convention, RNG consumption (randn_like + T-1 rand(1) per
+    forward), full-batch Adam -- against the reference's own 11-epoch run (tests/golden/vrae_generic.npz)."""
+    from vae_connexe_b200 import vrae as VR
+    g = np.load(os.path.join(GOLDEN, "vrae_generic.npz"))
+    torch.manual_seed(0)
+    data = torch.randn(48, 12, 10)
+    assert np.array_equal(data.numpy(), g["data"])
+    model = VR.VRAE(10, 64, 32, "gru", "tanh")
+    prm = O.gvrae_params_from_state_dict(model.state_dict())
+    for k in O.GVRAE_KEYS:
+        assert np.array_equal(prm[k].numpy(), g["init." + k]), k
+    assert np.array_equal(model.state_dict()["decoder.start_token"].numpy(), g["init.start_token"])
+    st = torch.get_rng_state()
+    recon, mu, logvar = model(data)
+    assert recon.shape == (48, 12, 10) and mu.shape == (48, 32)
+    assert _rel(recon, g["recon"]) < 1e-5 and _rel(mu, g["mu"]) < 1e-5 and _rel(logvar, g["logvar"]) < 1e-5
+    total, rec, kld = VR.VRAE.loss(recon, data, mu, logvar, 0.5)
+    assert abs(float(total) - float(g["total"])) < 1e-5 * float(g["total"])
+    model.engine.backward(0.5)
+    gr = model.engine.grad
+    assert _rel(gr["dec_w_ih"], g["grad.dec_w_ih"]) < 1e-5 and _rel(gr["enc_w_hh"], g["grad.enc_w_hh"]) < 1e-5
+    assert _rel(gr["z2h_w"], g["grad.z2h_w"]) < 1e-5 and _rel(gr["lat_w"][:32], g["grad.mu_w"]) < 1e-5
+    assert _rel(gr["out_w"], g["grad.out_w"]) < 1e-5 and _rel(gr["lat_b"][32:], g["grad.lv_b"]) < 1e-5
+    # fresh model, full training run
+    torch.manual_seed(0)
+    data = torch.randn(48, 12, 10)
+    model = VR.VRAE(10, 64, 32, "gru", "tanh")
+    log = []
+    VR.train(model, data, epochs=11, lr=1e-3, beta=0.5, log=log)
+    for i, r in enumerate(log):
+        assert abs(r["total"] - g["log_total"][i]) < 2e-4 and abs(r["rec"] - g["log_rec"][i]) < 2e-4 and abs(r["kld"] - g["log_kld"][i]) < 2e-4
+    prm = O.gvrae_params_from_state_dict(model.state_dict())
+    for k in O.GVRAE_KEYS:
+        assert _rel(prm[k], g["final." + k]) < 2e-5, k
+    assert np.array_equal(torch.get_rng_state().numpy(), g["rng_after"])
+    with pytest.raises(NotImplementedError):
+        model(data, teacher_forcing_ratio=0.5)
+    s = model.sample(4, 7)
+    assert s.shape == (4, 7, 10)

@@ -239,3 +239,19 @@ def test_cs_divergence_matches_reference():
     cs, dl, dm, dv = O.cs_head(lat, pm, pl, 0.1)
     assert abs(float(cs) - float(g["cs_vals"].mean())) < 1e-6
     assert np.array_equal(dl.numpy(), g["cs_dlat"]) and np.array_equal(dm.numpy(), g["cs_dpm"]) and np.array_equal(dv.numpy(), g["cs_dpl"])
+
+
+def test_generic_vrae_matches_reference():
+    """Config 4 (VRAE.py): oracle forward / loss / hand-derived backward vs the reference's autograd."""
+    g = np.load(os.path.join(GOLDEN, "vrae_generic.npz"))
+    prm = {k: torch.from_numpy(g["init." + k].copy()) for k in O.GVRAE_KEYS}
+    a = O.gvrae_forward(prm, torch.from_numpy(g["data"]), torch.from_numpy(g["eps"]), "tanh")
+    assert _rel(a["mu"].numpy(), g["mu"]) < 2e-6 and _rel(a["logvar"].numpy(), g["logvar"]) < 2e-6
+    assert _rel(a["recon"].permute(1, 0, 2).numpy(), g["recon"]) < 5e-6
+    l = O.gvrae_loss(a, 0.5)
+    assert abs(float(l["total"]) - float(g["total"])) < 2e-6 * float(g["total"])
+    assert abs(float(l["rec"]) - float(g["rec"])) < 2e-6 * float(g["rec"]) and abs(float(l["kld"]) - float(g["kld"])) < 2e-6 * float(g["kld"])
+    gr = O.gvrae_backward(prm, a, l, 0.5, "tanh")
+    for k in O.GVRAE_KEYS:
+        assert _rel(gr[k].numpy(), g["grad." + k]) < 1e-5, k
+    assert not bool(g["start_token_has_grad"])          # teacher forcing 1.0: the start token is never used (:79-82)

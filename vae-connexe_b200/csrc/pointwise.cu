@@ -26,13 +26,13 @@ __device__ double block_sum(double v, double* sh /* >= 32 doubles */) {
 __global__ void __launch_bounds__(1024) latent_fwd_kernel(const float* __restrict__ lat,
                                                           const float* __restrict__ eps,
                                                           float* __restrict__ z, float* __restrict__ kl_out,
-                                                          int B, int kl_form) {
+                                                          int B, int Z, int kl_form) {
     __shared__ double sh[32];
     double part = 0.0;
-    const int n = B * H;
+    const int n = B * Z;
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        int b = e / H, h = e % H;
-        float mu = lat[b * 2 * H + h], lv = lat[b * 2 * H + H + h];
+        int b = e / Z, h = e % Z;
+        float mu = lat[b * 2 * Z + h], lv = lat[b * 2 * Z + Z + h];
         float sigma = expf(__fmul_rn(0.5f, lv));
         z[e] = __fadd_rn(mu, __fmul_rn(sigma, eps[e]));
         float term;
@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(1024) latent_fwd_kernel(const float* __restric
 // dz = sum over heads of dh0 (+ peer partial); gradient into [mu | log_var]
 __global__ void latent_bwd_kernel(const float* __restrict__ dh0, int P, const float* __restrict__ dz_extra,
                                   const float* __restrict__ lat, const float* __restrict__ eps, float beta,
-                                  int kl_form, float* __restrict__ dlat, float* __restrict__ dz_out, int B) {
-    const int n = B * H;
+                                  int kl_form, float* __restrict__ dlat, float* __restrict__ dz_out, int B, int Z) {
+    const int n = B * Z;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     float dz = 0.f;
@@ -62,8 +62,8 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dh0, int P, const fl
     if (dz_out) dz_out[e] = dz;
     if (!dlat) return;
     if (dz_extra) dz += dz_extra[e];
-    const int b = e / H, h = e % H;
-    const float mu = lat[b * 2 * H + h], lv = lat[b * 2 * H + H + h];
+    const int b = e / Z, h = e % Z;
+    const float mu = lat[b * 2 * Z + h], lv = lat[b * 2 * Z + Z + h];
     const float invB = 1.f / (float)B;
     float dkl_mu, dkl_lv;
     if (kl_form == CRVAE_KL_SWAPPED) {
@@ -74,19 +74,19 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dh0, int P, const fl
         dkl_lv = -0.5f * (1.f - expf(lv)) * invB;
     }
     const float sigma = expf(0.5f * lv);
-    dlat[b * 2 * H + h] = dz + beta * dkl_mu;
-    dlat[b * 2 * H + H + h] = dz * eps[e] * 0.5f * sigma + beta * dkl_lv;
+    dlat[b * 2 * Z + h] = dz + beta * dkl_mu;
+    dlat[b * 2 * Z + Z + h] = dz * eps[e] * 0.5f * sigma + beta * dkl_lv;
 }
 
 // ---------------------------------------------------------------------------------------------
 // MSE forward + backward, one CTA per head (trainer :484 / :509, residual :599 / :639)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+__global__ void __launch_bounds__(1024) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                                   float* __restrict__ sse, float* __restrict__ dpred,
-                                                  float* __restrict__ err, int n) {
+                                                  float* __restrict__ err, int n, float dscale) {
     __shared__ double sh[32];
     const long long base = (long long)blockIdx.x * n;
-    const float scale = 2.f / (float)n;
+    const float scale = dscale > 0.f ? dscale : 2.f / (float)n;
     double part = 0.0;
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         float p = pred[base + e], t = target[base + e];
@@ -244,6 +244,21 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __res
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
         dx[e] = dy[e] * (1.f - y[e] * y[e]);
 }
+// generic output activation of VRAE.py's decoder (:60-68): kind 0 tanh, 1 sigmoid, 2 relu, 3 identity
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int kind) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float v = x[e];
+        y[e] = kind == 0 ? tanhf(v) : kind == 1 ? sigmoidf_acc(v) : kind == 2 ? fmaxf(v, 0.f) : v;
+    }
+}
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n,
+                               int kind) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float v = y[e];
+        const float gy = kind == 0 ? 1.f - v * v : kind == 1 ? v * (1.f - v) : kind == 2 ? (v > 0.f ? 1.f : 0.f) : 1.f;
+        dx[e] = dy[e] * gy;
+    }
+}
 // out[c][r] = in[r][c]  (small 2-D transpose through shared memory; err [P][T*B] <-> [T*B][P])
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
     __shared__ float tile[32][33];
@@ -267,29 +282,29 @@ static inline int grid_for(long long n, int block = 256, int cap = 148 * 8) {
 
 using namespace crvae;
 
-extern "C" int crvae_latent_fwd(const float* lat, const float* eps, float* z, float* kl_out, int B,
+extern "C" int crvae_latent_fwd(const float* lat, const float* eps, float* z, float* kl_out, int B, int Z,
                                 int kl_form, void* stream) {
-    CRVAE_REQUIRE(lat && eps && z && kl_out && B > 0, "bad argument");
-    latent_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lat, eps, z, kl_out, B, kl_form);
+    CRVAE_REQUIRE(lat && eps && z && kl_out && B > 0 && Z > 0, "bad argument");
+    latent_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lat, eps, z, kl_out, B, Z, kl_form);
     return check_launch("latent_fwd_kernel");
 }
 
 extern "C" int crvae_latent_bwd(const float* dh0, int P, const float* dz_extra, const float* lat,
                                 const float* eps, float beta, int kl_form, float* dlat, float* dz_out, int B,
-                                void* stream) {
-    CRVAE_REQUIRE(B > 0 && P >= 0 && (P == 0 || dh0), "bad argument");
+                                int Z, void* stream) {
+    CRVAE_REQUIRE(B > 0 && Z > 0 && P >= 0 && (P == 0 || dh0), "bad argument");
     CRVAE_REQUIRE(dlat == nullptr || (lat && eps), "lat/eps required with dlat");
-    int n = B * H;
+    int n = B * Z;
     latent_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dh0, P, dz_extra, lat, eps, beta, kl_form,
-                                                                         dlat, dz_out, B);
+                                                                         dlat, dz_out, B, Z);
     return check_launch("latent_bwd_kernel");
 }
 
 extern "C" int crvae_mse_fwd_bwd(const float* pred, const float* target, float* sse, float* dpred, float* err,
-                                 int P, int T, int B, void* stream) {
+                                 int P, int T, int B, float dscale, void* stream) {
     CRVAE_REQUIRE(pred && target && sse && P >= 0 && T > 0 && B > 0, "bad argument");
     if (P == 0) return 0;
-    mse_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(pred, target, sse, dpred, err, T * B);
+    mse_kernel<<<P, 1024, 0, (cudaStream_t)stream>>>(pred, target, sse, dpred, err, T * B, dscale);
     return check_launch("mse_kernel");
 }
 
@@ -375,4 +390,18 @@ extern "C" int crvae_adam_step_dev(float* theta, const float* grad, float* exp_a
     }
     incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter);
     return check_launch("incr_kernel");
+}
+
+extern "C" int crvae_act_fwd(const float* x, float* y, int64_t n, int kind, void* stream) {
+    CRVAE_REQUIRE(x && y && n >= 0 && kind >= 0 && kind <= 3, "bad argument");
+    if (n == 0) return 0;
+    act_fwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, kind);
+    return check_launch("act_fwd_kernel");
+}
+
+extern "C" int crvae_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int kind, void* stream) {
+    CRVAE_REQUIRE(dy && y && dx && n >= 0 && kind >= 0 && kind <= 3, "bad argument");
+    if (n == 0) return 0;
+    act_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n, kind);
+    return check_launch("act_bwd_kernel");
 }

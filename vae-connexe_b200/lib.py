@@ -34,10 +34,10 @@ SIGNATURES = {
     "crvae_gru_fwd_tc": (_c_int, [_c_void_p] * 6 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
     "crvae_gru_bwd_workspace": (_c_size_t, [_c_int] * 2),
     "crvae_gru_bwd": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 11 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
-    "crvae_latent_fwd": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_void_p]),
+    "crvae_latent_fwd": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_int, _c_void_p]),
     "crvae_latent_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_void_p,
-                                  _c_void_p, _c_int, _c_void_p]),
-    "crvae_mse_fwd_bwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p]),
+                                  _c_void_p, _c_int, _c_int, _c_void_p]),
+    "crvae_mse_fwd_bwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 3 + [_c_float, _c_void_p]),
     "crvae_gd_step": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_float, _c_void_p]),
     "crvae_gd_prox_gc": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_float, _c_float, _c_int, _c_void_p]),
     "crvae_adam_step": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_double] * 4 + [_c_int, _c_void_p]),
@@ -46,6 +46,8 @@ SIGNATURES = {
     "crvae_cs_div_fwd_bwd": (_c_int, [_c_void_p] * 3 + [_c_int, _c_int, _c_float] + [_c_void_p] * 6),
     "crvae_tanh_fwd": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_void_p]),
     "crvae_tanh_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p]),
+    "crvae_act_fwd": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_int, _c_void_p]),
+    "crvae_act_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_int, _c_void_p]),
     "crvae_transpose": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "crvae_sumsq": (_c_int, [_c_void_p, _c_i64, _c_void_p, _c_void_p]),
     "crvae_dot_small": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p]),
@@ -171,16 +173,16 @@ class Kernels:
                                         ptr(dpred), ptr(dh_last), ptr(dhs), ptr(dw_hh), ptr(db_hh), ptr(db_ih), ptr(dw_lin),
                                         ptr(db_lin), ptr(dh0), P, T, B, ptr(ws), stream_ptr()), "crvae_gru_bwd")
 
-    def latent_fwd(self, lat, eps, z, kl_out, B, kl_form):
-        self._ck(self.lib.crvae_latent_fwd(ptr(lat), ptr(eps), ptr(z), ptr(kl_out), B, kl_form, stream_ptr()),
+    def latent_fwd(self, lat, eps, z, kl_out, B, kl_form, Z=64):
+        self._ck(self.lib.crvae_latent_fwd(ptr(lat), ptr(eps), ptr(z), ptr(kl_out), B, Z, kl_form, stream_ptr()),
                  "crvae_latent_fwd")
 
-    def latent_bwd(self, dh0, P, dz_extra, lat, eps, beta, kl_form, dlat, dz_out, B):
+    def latent_bwd(self, dh0, P, dz_extra, lat, eps, beta, kl_form, dlat, dz_out, B, Z=64):
         self._ck(self.lib.crvae_latent_bwd(ptr(dh0), P, ptr(dz_extra), ptr(lat), ptr(eps), float(beta), kl_form,
-                                           ptr(dlat), ptr(dz_out), B, stream_ptr()), "crvae_latent_bwd")
+                                           ptr(dlat), ptr(dz_out), B, Z, stream_ptr()), "crvae_latent_bwd")
 
-    def mse_fwd_bwd(self, pred, target, sse, dpred, err, P, T, B):
-        self._ck(self.lib.crvae_mse_fwd_bwd(ptr(pred), ptr(target), ptr(sse), ptr(dpred), ptr(err), P, T, B,
+    def mse_fwd_bwd(self, pred, target, sse, dpred, err, P, T, B, dscale=0.0):
+        self._ck(self.lib.crvae_mse_fwd_bwd(ptr(pred), ptr(target), ptr(sse), ptr(dpred), ptr(err), P, T, B, float(dscale),
                                             stream_ptr()), "crvae_mse_fwd_bwd")
 
     def gd_step(self, theta, grad, n, lr):
@@ -211,6 +213,12 @@ class Kernels:
 
     def tanh_bwd(self, dy, y, dx, n):
         self._ck(self.lib.crvae_tanh_bwd(ptr(dy), ptr(y), ptr(dx), n, stream_ptr()), "crvae_tanh_bwd")
+
+    def act_fwd(self, x, y, n, kind):
+        self._ck(self.lib.crvae_act_fwd(ptr(x), ptr(y), n, kind, stream_ptr()), "crvae_act_fwd")
+
+    def act_bwd(self, dy, y, dx, n, kind):
+        self._ck(self.lib.crvae_act_bwd(ptr(dy), ptr(y), ptr(dx), n, kind, stream_ptr()), "crvae_act_bwd")
 
     def transpose(self, src, dst, rows, cols):
         self._ck(self.lib.crvae_transpose(ptr(src), ptr(dst), rows, cols, stream_ptr()), "crvae_transpose")
