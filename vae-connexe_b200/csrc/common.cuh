@@ -35,6 +35,14 @@ __device__ __forceinline__ float sigmoidf_acc(float x) {
     return __fdiv_rn(1.0f, 1.0f + expf(-x));
 }
 
+// Fast gate functions: ex2.approx + rcp.approx based, ~2-3 ulp (sigmoid) / ~1e-7 absolute (tanh).  The
+// layered parity protocol (P2/P3/P4, tests/test_gpu_train.py) stays green with them, GC included.
+// (branch-free: MUFU.EX2 + MUFU.RCP; __frcp_rn / __fdiv_rn would add a slow-path CALL per element)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoidf_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanhf_fast(float x) { return 1.0f - 2.0f * rcp_approx(ex2_approx(2.8853900817779268f * x) + 1.0f); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -116,9 +116,9 @@ __global__ void __launch_bounds__(256) gru_fwd_kernel(GruFwdArgs a) {
                 float ghr = acc[i][jj] + bhh[jj];
                 float ghz = acc[i][4 + jj] + bhh[4 + jj];
                 float ghn_ = acc[i][8 + jj] + bhh[8 + jj];
-                float r = sigmoidf_acc(gi[i][jj] + ghr);
-                float z = sigmoidf_acc(gi[i][4 + jj] + ghz);
-                float n = tanhf(__fadd_rn(gi[i][8 + jj], __fmul_rn(r, ghn_)));
+                float r = sigmoidf_fast(gi[i][jj] + ghr);
+                float z = sigmoidf_fast(gi[i][4 + jj] + ghz);
+                float n = tanhf_fast(__fadd_rn(gi[i][8 + jj], __fmul_rn(r, ghn_)));
                 float hold = hT[(j0 + jj) * HT_LD + ty * RB + i];
                 hnew[i][jj] = __fadd_rn(__fmul_rn(__fsub_rn(hold, n), z), n);
                 rr[i][jj] = r; zz[i][jj] = z; nn[i][jj] = n; gn[i][jj] = ghn_;

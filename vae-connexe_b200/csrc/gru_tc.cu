@@ -49,15 +49,6 @@ struct GruTcArgs {
     int P, T, B, t_skip;
 };
 
-__device__ __forceinline__ float fast_sigmoid(float x) {
-    // 1/(1+2^(-x*log2e)): ex2.approx + rcp.approx, ~2-3 ulp
-    return __frcp_rn(1.0f + __expf(-x));
-}
-__device__ __forceinline__ float fast_tanh(float x) {
-    // 1 - 2/(exp(2x)+1); absolute error ~1e-7 over the whole range, saturates cleanly
-    return 1.0f - 2.0f * __frcp_rn(__expf(2.0f * x) + 1.0f);
-}
-
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
@@ -212,7 +203,7 @@ gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
                     load_gi(0);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) rr[e] = fast_sigmoid(gi_v[e] + (acc_v[e] + bhh[jc + e]));
+                    for (int e = 0; e < 16; ++e) rr[e] = sigmoidf_fast(gi_v[e] + (acc_v[e] + bhh[jc + e]));
                     tmem_ld_32x16(acc + GH + jc, acc_v);
                     load_gi(1);
                     if (live) {
@@ -222,7 +213,7 @@ gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
                     }
                     tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) zz[e] = fast_sigmoid(gi_v[e] + (acc_v[e] + bhh[GH + jc + e]));
+                    for (int e = 0; e < 16; ++e) zz[e] = sigmoidf_fast(gi_v[e] + (acc_v[e] + bhh[GH + jc + e]));
                     tmem_ld_32x16(acc + 2 * GH + jc, acc_v);
                     load_gi(2);
                     if (live) {
@@ -234,7 +225,7 @@ gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const float ghn_ = acc_v[e] + bhh[2 * GH + jc + e];
-                        const float n = fast_tanh(__fadd_rn(gi_v[e], __fmul_rn(rr[e], ghn_)));
+                        const float n = tanhf_fast(__fadd_rn(gi_v[e], __fmul_rn(rr[e], ghn_)));
                         const float hn = __fadd_rn(__fmul_rn(__fsub_rn(h[jc + e], n), zz[e]), n);
                         h[jc + e] = hn;
                         acc_v[e] = ghn_;      // reuse: gh_n

@@ -7,11 +7,13 @@
 // into hi = tf32(v) and lo = v - hi (exact in fp32) and  A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi
 // is accumulated in fp32 in TMEM (the dropped Alo.Blo term is ~2^-22 relative).
 //
-// One CTA computes one [128 rows x 192 gate columns] tile = 128 (t,b) rows of one head:
+// Persistent kernel, one CTA per SM; a tile = [128 (t,b) rows x 192 gate columns] of one head:
 //   warp 0   : TMA producer  (4 boxes per 32-wide K chunk: A_hi, A_lo [128x32], B_hi, B_lo [192x32], SWIZZLE_128B)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per 8-wide K step)
-//   warps 2-5: epilogue, tcgen05.ld of the accumulator (lane = row) + bias -> global
-// smem ring: 2 stages x 80 KB, full/empty mbarriers; accumulator 128 lanes x 192 fp32 columns of TMEM.
+//   warps 2-5: epilogue, tcgen05.ld of the accumulator (lane = row), per-warp smem transpose, + bias -> global
+// smem ring: 2 stages x 80 KB, full/empty mbarriers; TWO accumulators of 128 lanes x 192 fp32 columns in TMEM
+// (tmem_full / tmem_empty mbarriers) so the epilogue of one tile overlaps the MMAs of the next.
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -24,31 +26,35 @@ constexpr int TC_STAGES = 2;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;    // 16384
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;    // 24576
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 81920
-constexpr int TC_TMEM_COLS = 256;
-constexpr int EPI_LD = TC_BN + 1;   // padded row of the epilogue transpose slab (floats)
-static_assert(4 * 32 * EPI_LD * 4 <= TC_STAGES * TC_STAGE_BYTES, "epilogue slabs must fit in the pipeline buffers");
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_TMEM_COLS = 512;   // two 192-column accumulators (double buffered)
+constexpr int EPI_LD = 33;          // padded row of the per-warp 32x32 epilogue transpose slab (floats)
+constexpr int TC_SLAB_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct ProjTcArgs {
     float* C;               // gates + t_skip*B*G
     const float* bias;      // [P][G]
     long long c_head_stride;
-    int M, K;
+    int M, K, n_mtiles, n_tiles;
 };
 
+// PERSISTENT: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  The TMA ring runs
+// continuously across tiles and the accumulator is double buffered in TMEM, so the epilogue of tile i (TMEM ->
+// registers -> per-warp smem transpose -> coalesced 128-byte stores) overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(192, 1)
 proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, ProjTcArgs a) {
     using namespace umma;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    float* slabs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_SLAB_BYTES);
     uint64_t* empty = full + TC_STAGES;
-    uint64_t* tmem_full = empty + TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + TC_STAGES;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, head = blockIdx.y;
     const int nchunks = (a.K + TC_BK - 1) / TC_BK;
 
     if (warp == 0 && lane == 0) {
@@ -57,7 +63,7 @@ proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            mbar_init(tmem_full, 1);
+            for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -70,72 +76,84 @@ proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* st = smem + s * TC_STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
-                tma_load_2d(st, &tmA_hi, &full[s], c * TC_BK, m_tile * TC_BM);
-                tma_load_2d(st + TC_A_BYTES, &tmA_lo, &full[s], c * TC_BK, m_tile * TC_BM);
-                tma_load_2d(st + 2 * TC_A_BYTES, &tmB_hi, &full[s], c * TC_BK, head * TC_BN);
-                tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full[s], c * TC_BK, head * TC_BN);
+            int c = 0;                                   // running chunk counter over all tiles of this CTA
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                const int head = tile / a.n_mtiles, m_tile = tile % a.n_mtiles;
+                for (int kc = 0; kc < nchunks; ++kc, ++c) {
+                    const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * TC_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
+                    tma_load_2d(st, &tmA_hi, &full[s], kc * TC_BK, m_tile * TC_BM);
+                    tma_load_2d(st + TC_A_BYTES, &tmA_lo, &full[s], kc * TC_BK, m_tile * TC_BM);
+                    tma_load_2d(st + 2 * TC_A_BYTES, &tmB_hi, &full[s], kc * TC_BK, head * TC_BN);
+                    tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmB_lo, &full[s], kc * TC_BK, head * TC_BN);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_tf32(TC_BM, TC_BN, false, false);
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            int c = 0, i = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++i) {
+                const int ab = i & 1;
+                mbar_wait(&tmem_empty[ab], ((i >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * TC_STAGE_BYTES);
-                const uint64_t a_hi = smem_desc_k_sw128(st), a_lo = smem_desc_k_sw128(st + TC_A_BYTES);
-                const uint64_t b_hi = smem_desc_k_sw128(st + 2 * TC_A_BYTES), b_lo = smem_desc_k_sw128(st + 2 * TC_A_BYTES + TC_B_BYTES);
-                int ksteps = (a.K - c * TC_BK + 7) / 8;
-                if (ksteps > TC_BK / 8) ksteps = TC_BK / 8;
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t adv = static_cast<uint64_t>(2 * k);        // 8 tf32 = 32 B = 2 x 16 B
-                    mma_tf32_ss(tmem_base, a_lo + adv, b_hi + adv, idesc, (c | k) != 0);
-                    mma_tf32_ss(tmem_base, a_hi + adv, b_lo + adv, idesc, true);
-                    mma_tf32_ss(tmem_base, a_hi + adv, b_hi + adv, idesc, true);
+                const uint32_t acc = tmem_base + static_cast<uint32_t>(ab * TC_BN);
+                for (int kc = 0; kc < nchunks; ++kc, ++c) {
+                    const int s = c % TC_STAGES, ph = (c / TC_STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + s * TC_STAGE_BYTES);
+                    const uint64_t a_hi = smem_desc_k_sw128(st), a_lo = smem_desc_k_sw128(st + TC_A_BYTES);
+                    const uint64_t b_hi = smem_desc_k_sw128(st + 2 * TC_A_BYTES), b_lo = smem_desc_k_sw128(st + 2 * TC_A_BYTES + TC_B_BYTES);
+                    int ksteps = (a.K - kc * TC_BK + 7) / 8;
+                    if (ksteps > TC_BK / 8) ksteps = TC_BK / 8;
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t adv = static_cast<uint64_t>(2 * k);        // 8 tf32 = 32 B = 2 x 16 B
+                        mma_tf32_ss(acc, a_lo + adv, b_hi + adv, idesc, (kc | k) != 0);
+                        mma_tf32_ss(acc, a_hi + adv, b_lo + adv, idesc, true);
+                        mma_tf32_ss(acc, a_hi + adv, b_hi + adv, idesc, true);
+                    }
+                    mma_commit(&empty[s]);          // smem stage is free once these MMAs have read it
                 }
-                mma_commit(&empty[s]);          // smem stage is free once these MMAs have read it
+                mma_commit(&tmem_full[ab]);         // accumulator complete
             }
-            mma_commit(tmem_full);              // accumulator complete
         }
     } else {
-        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        mbar_wait(tmem_full, 0);           // all MMAs done: accumulator complete AND the smem stages are idle
-        tc_fence_after();
-        // The accumulator arrives lane = row.  Writing rows straight out would make every store touch 32
-        // different lines, so each warp transposes its 32 x 192 slab through the (now idle) pipeline
-        // buffers: lane-per-row scalar stores into a padded tile (conflict-free), then row-by-row
-        // reads with lane = column -> fully coalesced 128-byte global stores with the bias added.
-        float* slab = reinterpret_cast<float*>(smem) + q * (32 * EPI_LD);
-        const float* bias = a.bias + static_cast<long long>(head) * TC_BN;
+        const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+        float* slab = slabs + q * (32 * EPI_LD);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++i) {
+            const int head = tile / a.n_mtiles, m_tile = tile % a.n_mtiles;
+            const int ab = i & 1;
+            mbar_wait(&tmem_full[ab], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * TC_BN);
+            const float* bias = a.bias + static_cast<long long>(head) * TC_BN;
+            const int row_base = m_tile * TC_BM + q * 32;
+            float* cbase = a.C + static_cast<long long>(head) * a.c_head_stride + static_cast<long long>(row_base) * TC_BN;
+            int nrows = a.M - row_base;
+            nrows = nrows < 0 ? 0 : (nrows > 32 ? 32 : nrows);
 #pragma unroll 1
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-            float v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), v);
-            tmem_ld_wait();
+            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(acc + static_cast<uint32_t>(c0), v);
+                tmem_ld_wait();
+                // lane = row in TMEM; transpose the 32x32 block through smem so every global store is one 128-byte line
 #pragma unroll
-            for (int j = 0; j < 32; ++j) slab[lane * EPI_LD + c0 + j] = v[j];
-        }
-        __syncwarp();
-        float bcol[TC_BN / 32];
-#pragma unroll
-        for (int i = 0; i < TC_BN / 32; ++i) bcol[i] = __ldg(bias + lane + 32 * i);
-        const int row_base = m_tile * TC_BM + q * 32;
-        float* cbase = a.C + static_cast<long long>(head) * a.c_head_stride + static_cast<long long>(row_base) * TC_BN;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-            if (row_base + rr < a.M) {
-#pragma unroll
-                for (int i = 0; i < TC_BN / 32; ++i)
-                    cbase[static_cast<long long>(rr) * TC_BN + lane + 32 * i] = slab[rr * EPI_LD + lane + 32 * i] + bcol[i];
+                for (int j = 0; j < 32; ++j) slab[lane * EPI_LD + j] = v[j];
+                __syncwarp();
+                const float bv = __ldg(bias + c0 + lane);
+#pragma unroll 8
+                for (int rr = 0; rr < nrows; ++rr)
+                    cbase[static_cast<long long>(rr) * TC_BN + c0 + lane] = slab[rr * EPI_LD + lane] + bv;
+                __syncwarp();
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[ab]);
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
@@ -250,8 +268,25 @@ extern "C" int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const flo
         if (e != cudaSuccess) { set_error("proj_fwd_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    ProjTcArgs a{gates + (long long)t_skip * B * TC_BN, b_ih, (long long)T * B * TC_BN, M, K};
-    dim3 grid((M + TC_BM - 1) / TC_BM, P);
+    const int n_mtiles = (M + TC_BM - 1) / TC_BM;
+    const int n_tiles = n_mtiles * P;
+    ProjTcArgs a{gates + (long long)t_skip * B * TC_BN, b_ih, (long long)T * B * TC_BN, M, K, n_mtiles, n_tiles};
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    // Leave a few SMs free when the grid would fill the machine: the latency-bound encoder chain runs concurrently
+    // on a high-priority stream (engine.py) and a persistent grid would otherwise starve it until this kernel ends.
+    static int reserve = -1;
+    if (reserve < 0) {
+        const char* e = getenv("CRVAE_PROJ_RESERVE_SMS");
+        reserve = e ? atoi(e) : 16;
+    }
+    int grid = n_tiles < num_sms ? n_tiles : num_sms;
+    if (n_tiles >= 2 * num_sms && grid > reserve + 8) grid -= reserve;
     proj_fwd_tc_kernel<<<grid, 192, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
     return check_launch("proj_fwd_tc_kernel");
 }
