@@ -141,6 +141,18 @@ int crvae_gru_bwd(float* gates, const float* ghn, const float* hs,
                   float* dw_hh, float* db_hh, float* db_ih, float* dw_lin, float* db_lin,
                   float* dh0, int P, int T, int B, void* workspace, void* stream);
 
+/* BPTT with the recurrent weight gradient deferred to the tensor cores: identical to crvae_gru_bwd except that
+ * dw_hh is NOT produced and `ghn` is overwritten in place with dgh_n = da_n*r; crvae_gru_dwhh_tc then computes
+ *   dw_hh[i][g][k] = sum_{t,b} dgh[i][t][b][g] * h_{t-1}[i][b][k]
+ * as one tcgen05 GEMM per head (3xTF32, MN-major operands read in place, tf32 split in shared memory).
+ * Needs B % 32 == 0.  Halves the FFMA work of the BPTT kernel and lets two of its CTAs share an SM.            */
+int crvae_gru_bwd_deferred(float* gates, float* ghn, const float* hs, const float* h0, int64_t h0_head_stride,
+                           const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
+                           const float* dhs, float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0,
+                           int P, int T, int B, void* workspace, void* stream);
+int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const float* hs, const float* h0,
+                      int64_t h0_head_stride, float* dw_hh, int P, int T, int B, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused reparameterisation + KL  (CRVAE.forward :210-216, VRAE4E.forward :157-163, trainer :486)
  *   lat [B,2Z] = [mu | log_var] (output of the fc_mu|fc_std GEMM);  eps [B,Z] ~ N(0,1)

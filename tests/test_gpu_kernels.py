@@ -180,6 +180,43 @@ def test_gru_forward_tensor_core(P, T, B, lin, t_skip, shared_h0):
         assert _rel(out[name], ref[name]) < 2e-5, (name, _rel(out[name], ref[name]))
 
 
+@pytest.mark.parametrize("P,T,B,lin,shared_h0", [(3, 10, 256, True, True), (2, 5, 64, False, False), (20, 10, 256, True, True),
+                                                  (1, 10, 32, True, True)])
+def test_gru_backward_deferred_dwhh_tensor_core(P, T, B, lin, shared_h0):
+    """BPTT with dW_hh deferred to a tcgen05 GEMM (crvae_gru_bwd_deferred + crvae_gru_dwhh_tc) against the oracle and
+    against the in-kernel FFMA accumulation."""
+    k, o = _k(), OracleKernels()
+    gi = _rand(P, T, B, G, seed=1)
+    b_ih, w_hh, b_hh = _rand(P, G, seed=2, scale=0.2), _rand(P, G, H, seed=3, scale=0.125), _rand(P, G, seed=4, scale=0.2)
+    h0 = _rand(B, H, seed=5) if shared_h0 else _rand(P, B, H, seed=5)
+    stride = 0 if shared_h0 else B * H
+    w_lin, b_lin = (_rand(P, H, seed=6, scale=0.2), _rand(P, seed=7)) if lin else (None, None)
+    c = lambda t: None if t is None else t.cuda()
+    fw = dict(g=gi.clone(), hs=torch.zeros(P, T, B, H), ghn=torch.zeros(P, T, B, H), pred=torch.zeros(P, T, B) if lin else None)
+    o.gru_fwd(fw["g"], b_ih, w_hh, b_hh, h0, stride, w_lin, b_lin, fw["hs"], fw["ghn"], fw["pred"], P, T, B, 0)
+    dpred = _rand(P, T, B, seed=8) if lin else None
+    dh_last, dhs = _rand(P, B, H, seed=9, scale=0.1), _rand(P, T, B, H, seed=10, scale=0.1)
+    z = lambda *s: torch.zeros(*s)
+    ref = dict(g=fw["g"].clone(), dw_hh=z(P, G, H), db_hh=z(P, G), db_ih=z(P, G), dw_lin=z(P, H) if lin else None,
+               db_lin=z(P) if lin else None, dh0=z(P, B, H))
+    o.gru_bwd(ref["g"], fw["ghn"], fw["hs"], h0, stride, w_hh, w_lin, dpred, dh_last, dhs, ref["dw_hh"], ref["db_hh"], ref["db_ih"],
+              ref["dw_lin"], ref["db_lin"], ref["dh0"], P, T, B, None)
+    gpu = {n: (None if v is None else torch.zeros_like(v).cuda()) for n, v in ref.items()}
+    gpu["g"] = fw["g"].clone().cuda()
+    ghn = fw["ghn"].clone().cuda()
+    ws = torch.zeros(k.gru_bwd_workspace(P, B) // 4 + 4, device="cuda")
+    k.gru_bwd_deferred(gpu["g"], ghn, c(fw["hs"]), c(h0), stride, c(w_hh), c(w_lin), c(dpred), c(dh_last), c(dhs), gpu["db_hh"],
+                       gpu["db_ih"], gpu["dw_lin"], gpu["db_lin"], gpu["dh0"], P, T, B, ws)
+    k.gru_dwhh_tc(gpu["g"], ghn, c(fw["hs"]), c(h0), stride, gpu["dw_hh"], P, T, B)
+    torch.cuda.synchronize()
+    for name, v in ref.items():
+        if v is not None:
+            assert _rel(gpu[name], v) < 5e-5, (name, _rel(gpu[name], v))
+    # dgh_n left in the ghn buffer = dgi_n * r
+    r_ = fw["g"][..., :H]
+    assert _rel(ghn, ref["g"][..., 2 * H:] * r_) < 5e-5
+
+
 @pytest.mark.parametrize("form", [0, 1])
 @pytest.mark.parametrize("B", [64, 256])
 def test_latent_fwd_bwd(form, B):

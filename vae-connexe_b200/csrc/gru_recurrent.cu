@@ -162,6 +162,7 @@ struct GruBwdArgs {
     const float* dpred; const float* dh_last; const float* dhs;
     float* dh0; float* ws;
     int P, T, B, ntiles;
+    float* dghn_out;      // DEFER_DW: receives dgh_n = da_n * r (may alias ghn: each element is read before it is written)
 };
 
 constexpr int WS_TILE = G * H + 512;   // floats per (head, tile) partial: dW_hh | db_ih | db_hh | dw_lin | db_lin
@@ -170,8 +171,11 @@ constexpr int WS_DBHH = G * H + G;
 constexpr int WS_DWLIN = G * H + 2 * G;
 constexpr int WS_DBLIN = G * H + 2 * G + H;
 
-template <int RB>
-__global__ void __launch_bounds__(256) gru_bwd_kernel(GruBwdArgs a) {
+// DEFER_DW = true: the dW_hh accumulation is NOT done here (crvae_gru_dwhh_tc does it as one tensor-core GEMM per head);
+// the kernel then writes dgh_n for that GEMM, needs neither the 48 accumulator registers nor the h_{t-1} tile, and two
+// CTAs fit on an SM.
+template <int RB, bool DEFER_DW>
+__global__ void __launch_bounds__(256, DEFER_DW ? 2 : 1) gru_bwd_kernel(GruBwdArgs a) {
     constexpr int BT = 16 * RB;
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;                        // [G][H]      natural layout
@@ -284,7 +288,11 @@ __global__ void __launch_bounds__(256) gru_bwd_kernel(GruBwdArgs a) {
             *reinterpret_cast<float4*>(drow) = make_float4(dar[0], dar[1], dar[2], dar[3]);
             *reinterpret_cast<float4*>(drow + H) = make_float4(daz[0], daz[1], daz[2], daz[3]);
             *reinterpret_cast<float4*>(drow + 2 * H) = make_float4(dghn[0], dghn[1], dghn[2], dghn[3]);
-            *reinterpret_cast<float4*>(Hp + lb * HP_LD + j0) = hp4;
+            if (DEFER_DW) {
+                if (gb < a.B) *reinterpret_cast<float4*>(a.dghn_out + (row0 + gb) * H + j0) = make_float4(dghn[0], dghn[1], dghn[2], dghn[3]);
+            } else {
+                *reinterpret_cast<float4*>(Hp + lb * HP_LD + j0) = hp4;
+            }
         }
         __syncthreads();
         // ---- matmul 1: dh_{t-1}[b][k] = dh_t*z + sum_g dgh[b][g] * W_hh[g][k] ----
@@ -311,6 +319,7 @@ __global__ void __launch_bounds__(256) gru_bwd_kernel(GruBwdArgs a) {
             }
         }
         // ---- matmul 2: dW_hh[g][k] += sum_b dgh[b][g] * h_{t-1}[b][k]   (g = g0.., k = j0..) ----
+        if (!DEFER_DW)
 #pragma unroll 2
         for (int b = 0; b < BT; ++b) {
             float4 hp = *reinterpret_cast<const float4*>(&Hp[b * HP_LD + j0]);
@@ -340,9 +349,11 @@ __global__ void __launch_bounds__(256) gru_bwd_kernel(GruBwdArgs a) {
                 make_float4(dh[i][0], dh[i][1], dh[i][2], dh[i][3]);
     }
     float* ws = a.ws + ((long long)head * a.ntiles + tile) * WS_TILE;
+    if (!DEFER_DW) {
 #pragma unroll
-    for (int q = 0; q < 12; ++q)
-        *reinterpret_cast<float4*>(ws + (g0 + q) * H + j0) = make_float4(dW[q][0], dW[q][1], dW[q][2], dW[q][3]);
+        for (int q = 0; q < 12; ++q)
+            *reinterpret_cast<float4*>(ws + (g0 + q) * H + j0) = make_float4(dW[q][0], dW[q][1], dW[q][2], dW[q][3]);
+    }
     // column sums over the 16 row groups (ty) through shared memory (Ds is free after the last sync)
     float* red = Ds;                       // [16 ty][16 tx][24]
     float* mine = red + (ty * 16 + tx) * 24;
@@ -379,9 +390,10 @@ __global__ void gru_bwd_finalize_kernel(GruFinArgs a) {
     const int head = blockIdx.y;
     const float* ws = a.ws + (long long)head * a.ntiles * WS_TILE;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e <= WS_DBLIN; e += gridDim.x * blockDim.x) {
+        if (e < WS_DBIH && !a.dw_hh) continue;
         float s = 0.f;
         for (int k = 0; k < a.ntiles; ++k) s += ws[(long long)k * WS_TILE + e];
-        if (e < WS_DBIH) a.dw_hh[(long long)head * G * H + e] = s;
+        if (e < WS_DBIH) { if (a.dw_hh) a.dw_hh[(long long)head * G * H + e] = s; }
         else if (e < WS_DBHH) a.db_ih[(long long)head * G + (e - WS_DBIH)] = s;
         else if (e < WS_DWLIN) a.db_hh[(long long)head * G + (e - WS_DBHH)] = s;
         else if (e < WS_DBLIN) { if (a.dw_lin) a.dw_lin[(long long)head * H + (e - WS_DWLIN)] = s; }
@@ -413,20 +425,20 @@ static int launch_fwd(const GruFwdArgs& a, cudaStream_t st) {
     return check_launch("gru_fwd_kernel");
 }
 
-template <int RB>
+template <int RB, bool DEFER_DW>
 static int launch_bwd(const GruBwdArgs& a, cudaStream_t st) {
     constexpr int BT = 16 * RB;
-    size_t smem = (size_t)(G * H + BT * D_LD + BT * HP_LD) * sizeof(float);
+    size_t smem = (size_t)(G * H + BT * D_LD + (DEFER_DW ? 0 : BT * HP_LD)) * sizeof(float);
     size_t red = (size_t)(G * H + 256 * 24) * sizeof(float);
     if (smem < red) smem = red;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gru_bwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gru_bwd_kernel<RB, DEFER_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("gru_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
     dim3 grid(a.ntiles, a.P);
-    gru_bwd_kernel<RB><<<grid, 256, smem, st>>>(a);
+    gru_bwd_kernel<RB, DEFER_DW><<<grid, 256, smem, st>>>(a);
     return check_launch("gru_bwd_kernel");
 }
 
@@ -460,31 +472,60 @@ extern "C" size_t crvae_gru_bwd_workspace(int P, int B) {
     return (size_t)(P > 0 ? P : 1) * ((B + 15) / 16) * WS_TILE * sizeof(float);
 }
 
-extern "C" int crvae_gru_bwd(float* gates, const float* ghn, const float* hs, const float* h0,
-                             int64_t h0_head_stride, const float* w_hh, const float* w_lin,
-                             const float* dpred, const float* dh_last, const float* dhs, float* dw_hh,
-                             float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0, int P, int T,
-                             int B, void* workspace, void* stream) {
-    CRVAE_REQUIRE(gates && ghn && hs && h0 && w_hh && dw_hh && db_hh && db_ih && dh0 && workspace, "null operand");
+static int gru_bwd_impl(float* gates, float* ghn, const float* hs, const float* h0, int64_t h0_head_stride, const float* w_hh,
+                        const float* w_lin, const float* dpred, const float* dh_last, const float* dhs, float* dw_hh,
+                        float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0, int P, int T, int B,
+                        void* workspace, void* stream, bool defer_dw) {
+    CRVAE_REQUIRE(gates && ghn && hs && h0 && w_hh && db_hh && db_ih && dh0 && workspace, "null operand");
+    CRVAE_REQUIRE(defer_dw || dw_hh, "dw_hh missing");
     CRVAE_REQUIRE((w_lin == nullptr) == (dpred == nullptr), "w_lin and dpred go together");
     CRVAE_REQUIRE(w_lin == nullptr || (dw_lin && db_lin), "dw_lin/db_lin missing");
     CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0, "bad size");
     CRVAE_REQUIRE(aligned16(gates) && aligned16(hs) && aligned16(ghn) && aligned16(h0) && aligned16(dh0) &&
                   aligned16(workspace), "16-byte alignment");
+    CRVAE_REQUIRE(dhs == nullptr || aligned16(dhs), "16-byte alignment");
     if (P == 0) return 0;
     int rb = g_force_rb ? g_force_rb : choose_rb(P, B);
     int ntiles = (B + 16 * rb - 1) / (16 * rb);
-    CRVAE_REQUIRE(dhs == nullptr || aligned16(dhs), "16-byte alignment");
     GruBwdArgs a{gates, ghn, hs, h0, (long long)h0_head_stride, w_hh, w_lin, dpred, dh_last, dhs, dh0,
-                 (float*)workspace, P, T, B, ntiles};
+                 (float*)workspace, P, T, B, ntiles, defer_dw ? ghn : nullptr};
     int rc;
-    switch (rb) {
-        case 4: rc = launch_bwd<4>(a, (cudaStream_t)stream); break;
-        case 2: rc = launch_bwd<2>(a, (cudaStream_t)stream); break;
-        default: rc = launch_bwd<1>(a, (cudaStream_t)stream); break;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (defer_dw) {
+        switch (rb) {
+            case 4: rc = launch_bwd<4, true>(a, st); break;
+            case 2: rc = launch_bwd<2, true>(a, st); break;
+            default: rc = launch_bwd<1, true>(a, st); break;
+        }
+    } else {
+        switch (rb) {
+            case 4: rc = launch_bwd<4, false>(a, st); break;
+            case 2: rc = launch_bwd<2, false>(a, st); break;
+            default: rc = launch_bwd<1, false>(a, st); break;
+        }
     }
     if (rc) return rc;
-    GruFinArgs f{(const float*)workspace, dw_hh, db_hh, db_ih, dw_lin, db_lin, ntiles};
-    gru_bwd_finalize_kernel<<<dim3((WS_DBLIN + 256) / 256, P), 256, 0, (cudaStream_t)stream>>>(f);
+    GruFinArgs f{(const float*)workspace, defer_dw ? nullptr : dw_hh, db_hh, db_ih, dw_lin, db_lin, ntiles};
+    gru_bwd_finalize_kernel<<<dim3((WS_DBLIN + 256) / 256, P), 256, 0, st>>>(f);
     return check_launch("gru_bwd_finalize_kernel");
+}
+
+extern "C" int crvae_gru_bwd(float* gates, const float* ghn, const float* hs, const float* h0,
+                             int64_t h0_head_stride, const float* w_hh, const float* w_lin,
+                             const float* dpred, const float* dh_last, const float* dhs, float* dw_hh,
+                             float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0, int P, int T,
+                             int B, void* workspace, void* stream) {
+    return gru_bwd_impl(gates, const_cast<float*>(ghn), hs, h0, h0_head_stride, w_hh, w_lin, dpred, dh_last, dhs, dw_hh, db_hh,
+                        db_ih, dw_lin, db_lin, dh0, P, T, B, workspace, stream, false);
+}
+
+// Same BPTT with the dW_hh accumulation deferred: `ghn` is overwritten IN PLACE with dgh_n = da_n*r and dw_hh is not
+// produced here -- follow with crvae_gru_dwhh_tc(gates, ghn, hs, h0, ...).
+extern "C" int crvae_gru_bwd_deferred(float* gates, float* ghn, const float* hs, const float* h0,
+                                      int64_t h0_head_stride, const float* w_hh, const float* w_lin,
+                                      const float* dpred, const float* dh_last, const float* dhs,
+                                      float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0, int P, int T,
+                                      int B, void* workspace, void* stream) {
+    return gru_bwd_impl(gates, ghn, hs, h0, h0_head_stride, w_hh, w_lin, dpred, dh_last, dhs, nullptr, db_hh, db_ih, dw_lin,
+                        db_lin, dh0, P, T, B, workspace, stream, true);
 }

@@ -103,6 +103,8 @@ class CRVAEEngine:
         self.kl_form = L.KL_SWAPPED
         self._side = None
         self.use_side_stream = True
+        import os as _os2
+        self.bwd_mode = _os2.environ.get("CRVAE_BWD_MODE", "defer")     # "defer" (dW_hh on tcgen05) | "fused" (in-kernel FFMA)
 
     # ------------------------------------------------------------------ batch binding
     def bind_batch(self, X: torch.Tensor):
@@ -261,7 +263,13 @@ class CRVAEEngine:
     def backward(self, beta: float, lam_ridge: float = 0.0, dlat_extra: Optional[torch.Tensor] = None):
         """Gradient of smooth = loss + ridge + beta*KL (:489/:515) into the grad arena (:497)."""
         k, th, g, B, P, p_ = self.k, self.theta, self.grad, self.B, self.P, self.p
-        if P > 0:
+        # decoder BPTT.  With enough heads the dW_hh accumulation is deferred to one tcgen05 GEMM per head
+        # (crvae_gru_dwhh_tc, issued below next to the projection weight gradient): half the FFMA work, 2 CTAs per SM.
+        defer = P >= 8 and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
+        if P > 0 and defer:
+            k.gru_bwd_deferred(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
+                               g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
+        elif P > 0:
             k.gru_bwd(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
                       g["w_hh"], g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
         # The latent / encoder backward chain (small, latency-bound) goes to the high-priority side stream;
@@ -288,6 +296,8 @@ class CRVAEEngine:
                       1, ENC_STEPS, B, self.ws_gru_enc)
             k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
         if P > 0:
+            if defer:
+                k.gru_dwhh_tc(self.gates, self.ghn, self.hs, self.zlat, 0, g["w_hh"], P, DEC_STEPS, B)
             if self.proj_mode == "tc3":
                 k.proj_wgrad_tc(self.gates, self.dec_in_hi, self.dec_in_lo, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1)
             else:

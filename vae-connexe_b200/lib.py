@@ -34,6 +34,8 @@ SIGNATURES = {
     "crvae_gru_fwd_tc": (_c_int, [_c_void_p] * 6 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
     "crvae_gru_bwd_workspace": (_c_size_t, [_c_int] * 2),
     "crvae_gru_bwd": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 11 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
+    "crvae_gru_bwd_deferred": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 10 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
+    "crvae_gru_dwhh_tc": (_c_int, [_c_void_p] * 4 + [_c_i64, _c_void_p] + [_c_int] * 3 + [_c_void_p]),
     "crvae_latent_fwd": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_int, _c_void_p]),
     "crvae_latent_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_void_p,
                                   _c_void_p, _c_int, _c_int, _c_void_p]),
@@ -172,6 +174,16 @@ class Kernels:
         self._ck(self.lib.crvae_gru_bwd(ptr(gates), ptr(ghn), ptr(hs), ptr(h0), h0_stride, ptr(w_hh), ptr(w_lin),
                                         ptr(dpred), ptr(dh_last), ptr(dhs), ptr(dw_hh), ptr(db_hh), ptr(db_ih), ptr(dw_lin),
                                         ptr(db_lin), ptr(dh0), P, T, B, ptr(ws), stream_ptr()), "crvae_gru_bwd")
+
+    def gru_bwd_deferred(self, gates, ghn, hs, h0, h0_stride, w_hh, w_lin, dpred, dh_last, dhs, db_hh, db_ih, dw_lin, db_lin,
+                         dh0, P, T, B, ws):
+        self._ck(self.lib.crvae_gru_bwd_deferred(ptr(gates), ptr(ghn), ptr(hs), ptr(h0), h0_stride, ptr(w_hh), ptr(w_lin),
+                                                 ptr(dpred), ptr(dh_last), ptr(dhs), ptr(db_hh), ptr(db_ih), ptr(dw_lin),
+                                                 ptr(db_lin), ptr(dh0), P, T, B, ptr(ws), stream_ptr()), "crvae_gru_bwd_deferred")
+
+    def gru_dwhh_tc(self, dgates, dghn, hs, h0, h0_stride, dw_hh, P, T, B):
+        self._ck(self.lib.crvae_gru_dwhh_tc(ptr(dgates), ptr(dghn), ptr(hs), ptr(h0), h0_stride, ptr(dw_hh), P, T, B,
+                                            stream_ptr()), "crvae_gru_dwhh_tc")
 
     def latent_fwd(self, lat, eps, z, kl_out, B, kl_form, Z=64):
         self._ck(self.lib.crvae_latent_fwd(ptr(lat), ptr(eps), ptr(z), ptr(kl_out), B, Z, kl_form, stream_ptr()),
