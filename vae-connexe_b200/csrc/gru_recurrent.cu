@@ -32,7 +32,7 @@ struct GruFwdArgs {
 // for all three gates -> RB x 12 accumulators.
 // ------------------------------------------------------------------------------------------
 template <int RB>
-__global__ void __launch_bounds__(256) gru_fwd_kernel(GruFwdArgs a) {
+__global__ void __launch_bounds__(256, 2) gru_fwd_kernel(GruFwdArgs a) {
     constexpr int BT = 16 * RB;
     constexpr int HT_LD = BT + 4;
     extern __shared__ __align__(16) float smem[];
@@ -70,22 +70,6 @@ __global__ void __launch_bounds__(256) gru_fwd_kernel(GruFwdArgs a) {
 
     for (int t = 0; t < a.T; ++t) {
         const long long row0 = ((long long)head * a.T + t) * a.B;   // row index of b = 0
-        float gi[RB][12];
-#pragma unroll
-        for (int i = 0; i < RB; ++i) {
-            int gb = b_tile + ty * RB + i;
-            if (t < a.t_skip || gb >= a.B) {
-#pragma unroll
-                for (int q = 0; q < 12; ++q) gi[i][q] = bih[q];
-            } else {
-                const float* src = a.gates + (row0 + gb) * G + j0;
-#pragma unroll
-                for (int gt = 0; gt < 3; ++gt) {
-                    float4 v = *reinterpret_cast<const float4*>(src + gt * H);
-                    gi[i][gt * 4 + 0] = v.x; gi[i][gt * 4 + 1] = v.y; gi[i][gt * 4 + 2] = v.z; gi[i][gt * 4 + 3] = v.w;
-                }
-            }
-        }
         float acc[RB][12];
 #pragma unroll
         for (int i = 0; i < RB; ++i)
@@ -106,6 +90,24 @@ __global__ void __launch_bounds__(256) gru_fwd_kernel(GruFwdArgs a) {
             for (int i = 0; i < RB; ++i)
 #pragma unroll
                 for (int q = 0; q < 12; ++q) acc[i][q] = fmaf(hv[i], w[q], acc[i][q]);
+        }
+        // gi is fetched AFTER the matmul: its latency is covered by the second CTA resident on the SM, and not
+        // holding 12*RB registers across the K loop is what lets two CTAs fit (<= 128 registers per thread)
+        float gi[RB][12];
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            int gb = b_tile + ty * RB + i;
+            if (t < a.t_skip || gb >= a.B) {
+#pragma unroll
+                for (int q = 0; q < 12; ++q) gi[i][q] = bih[q];
+            } else {
+                const float* src = a.gates + (row0 + gb) * G + j0;
+#pragma unroll
+                for (int gt = 0; gt < 3; ++gt) {
+                    float4 v = *reinterpret_cast<const float4*>(src + gt * H);
+                    gi[i][gt * 4 + 0] = v.x; gi[i][gt * 4 + 1] = v.y; gi[i][gt * 4 + 2] = v.z; gi[i][gt * 4 + 3] = v.w;
+                }
+            }
         }
         // gate math; operation order h' = (h - n)*z + n reproduces ATen's CPU GRU
         float hnew[RB][4], rr[RB][4], zz[RB][4], nn[RB][4], gn[RB][4];
