@@ -22,7 +22,7 @@ int make_tmap_generic(CUtensorMap* m, const float* base, int rank, const uint64_
 
 constexpr int DH_H = CRVAE_HIDDEN;
 constexpr int DH_G = CRVAE_G;
-constexpr int DH_BK = 32;                          // reduction rows per stage
+constexpr int DH_BK = 32;                          // reduction rows per stage (16 x 6 stages measured slower: 125 vs 110 us)
 constexpr int DH_STAGES = 3;
 constexpr int DH_BLOCK = DH_BK * 128;              // 4096 B: one MN-block (32 elements wide) of a stage = LBO
 constexpr int DH_OFF_A0 = 0;                       // 4 blocks: g 0..127

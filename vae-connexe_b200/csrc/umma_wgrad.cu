@@ -28,10 +28,10 @@ int make_tmap_generic(CUtensorMap* m, const float* base, int rank, const uint64_
 
 constexpr int WG_BM = 128;                 // input columns k per tile (UMMA M, TMEM lanes)
 constexpr int WG_BN = CRVAE_G;             // 192 gate rows (UMMA N, TMEM columns)
-constexpr int WG_BK = 32;                  // reduction rows (m) per stage
-constexpr int WG_STAGES = 2;
-constexpr int WG_A_BYTES = WG_BM * WG_BK * 4;          // 16384: 4 MN-blocks x [32 rows x 128 B]
-constexpr int WG_B_BYTES = WG_BN * WG_BK * 4;          // 24576: 6 MN-blocks x [32 rows x 128 B]
+constexpr int WG_BK = 16;                  // reduction rows (m) per stage (more, smaller stages: deeper TMA pipeline)
+constexpr int WG_STAGES = 4;
+constexpr int WG_A_BYTES = WG_BM * WG_BK * 4;          // 4 MN-blocks x [WG_BK rows x 128 B]
+constexpr int WG_B_BYTES = WG_BN * WG_BK * 4;          // 6 MN-blocks x [WG_BK rows x 128 B]
 constexpr int WG_BLOCK_BYTES = WG_BK * 128;            // 4096: one MN-block (32 M/N elements) of a stage = LBO
 constexpr int WG_STAGE_BYTES = 2 * WG_A_BYTES + 2 * WG_B_BYTES;
 constexpr int WG_TX_BYTES = 2 * WG_A_BYTES + WG_B_BYTES;   // bytes landed by TMA per stage (B_lo is produced in smem)
