@@ -119,10 +119,16 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
                     float4 v = *reinterpret_cast<const float4*>(&Bs[kk][tile_index<TN>(tx, j, BN)]);
                     b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
                 }
+                // packed fp32 FMA (FFMA2, fma.rn.f32x2): Blackwell's full-rate fp32 path; bit-identical per component
 #pragma unroll
-                for (int i = 0; i < TM; ++i)
+                for (int i = 0; i < TM; ++i) {
+                    const float2 a2 = make_float2(a[i], a[i]);
 #pragma unroll
-                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    for (int j = 0; j < TN; j += 2) {
+                        float2 r = __ffma2_rn(a2, make_float2(b[j], b[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
+                        acc[i][j] = r.x; acc[i][j + 1] = r.y;
+                    }
+                }
             }
             __syncthreads();
         }

@@ -70,27 +70,35 @@ __global__ void __launch_bounds__(256, 2) gru_fwd_kernel(GruFwdArgs a) {
 
     for (int t = 0; t < a.T; ++t) {
         const long long row0 = ((long long)head * a.T + t) * a.B;   // row index of b = 0
-        float acc[RB][12];
+        // Blackwell issues fp32 FMAs at full rate only as packed pairs (FFMA2, fma.rn.f32x2): accumulators are float2
+        // over adjacent gate columns, the hidden value is broadcast into both halves.  Per-component results are
+        // bit-identical to scalar fmaf.
+        float2 acc2[RB][6];
 #pragma unroll
         for (int i = 0; i < RB; ++i)
 #pragma unroll
-            for (int q = 0; q < 12; ++q) acc[i][q] = 0.f;
+            for (int q = 0; q < 6; ++q) acc2[i][q] = make_float2(0.f, 0.f);
 #pragma unroll 4
         for (int k = 0; k < H; ++k) {
-            float hv[RB];
+            float2 hv2[RB];
 #pragma unroll
-            for (int i = 0; i < RB; ++i) hv[i] = hT[k * HT_LD + ty * RB + i];
-            float w[12];
+            for (int i = 0; i < RB; ++i) { const float v = hT[k * HT_LD + ty * RB + i]; hv2[i] = make_float2(v, v); }
+            float2 w2[6];
 #pragma unroll
             for (int gt = 0; gt < 3; ++gt) {
                 float4 v = *reinterpret_cast<const float4*>(&Wt[k * WT_LD + gt * H + j0]);
-                w[gt * 4 + 0] = v.x; w[gt * 4 + 1] = v.y; w[gt * 4 + 2] = v.z; w[gt * 4 + 3] = v.w;
+                w2[gt * 2] = make_float2(v.x, v.y); w2[gt * 2 + 1] = make_float2(v.z, v.w);
             }
 #pragma unroll
             for (int i = 0; i < RB; ++i)
 #pragma unroll
-                for (int q = 0; q < 12; ++q) acc[i][q] = fmaf(hv[i], w[q], acc[i][q]);
+                for (int q = 0; q < 6; ++q) acc2[i][q] = __ffma2_rn(hv2[i], w2[q], acc2[i][q]);
         }
+        float acc[RB][12];
+#pragma unroll
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { acc[i][2 * q] = acc2[i][q].x; acc[i][2 * q + 1] = acc2[i][q].y; }
         // gi is fetched AFTER the matmul: its latency is covered by the second CTA resident on the SM, and not
         // holding 12*RB registers across the K loop is what lets two CTAs fit (<= 128 registers per thread)
         float gi[RB][12];
@@ -298,28 +306,31 @@ __global__ void __launch_bounds__(256, DEFER_DW ? 2 : 1) gru_bwd_kernel(GruBwdAr
         }
         __syncthreads();
         // ---- matmul 1: dh_{t-1}[b][k] = dh_t*z + sum_g dgh[b][g] * W_hh[g][k] ----
+        float2 dh2[RB][2];
 #pragma unroll
-        for (int i = 0; i < RB; ++i)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) dh[i][jj] = dhz[i][jj];
+        for (int i = 0; i < RB; ++i) { dh2[i][0] = make_float2(dhz[i][0], dhz[i][1]); dh2[i][1] = make_float2(dhz[i][2], dhz[i][3]); }
 #pragma unroll 2
         for (int g = 0; g < G; g += 4) {
-            float4 w[4];
+            float2 w2[4][2];
 #pragma unroll
-            for (int gg = 0; gg < 4; ++gg) w[gg] = *reinterpret_cast<const float4*>(&Ws[(g + gg) * H + j0]);
+            for (int gg = 0; gg < 4; ++gg) {
+                float4 v = *reinterpret_cast<const float4*>(&Ws[(g + gg) * H + j0]);
+                w2[gg][0] = make_float2(v.x, v.y); w2[gg][1] = make_float2(v.z, v.w);
+            }
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
                 float4 d = *reinterpret_cast<const float4*>(&Ds[(ty * RB + i) * D_LD + g]);
                 const float dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
                 for (int gg = 0; gg < 4; ++gg) {
-                    dh[i][0] = fmaf(dv[gg], w[gg].x, dh[i][0]);
-                    dh[i][1] = fmaf(dv[gg], w[gg].y, dh[i][1]);
-                    dh[i][2] = fmaf(dv[gg], w[gg].z, dh[i][2]);
-                    dh[i][3] = fmaf(dv[gg], w[gg].w, dh[i][3]);
+                    const float2 d2 = make_float2(dv[gg], dv[gg]);
+                    dh2[i][0] = __ffma2_rn(d2, w2[gg][0], dh2[i][0]);     // packed fp32 FMA (FFMA2)
+                    dh2[i][1] = __ffma2_rn(d2, w2[gg][1], dh2[i][1]);
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) { dh[i][0] = dh2[i][0].x; dh[i][1] = dh2[i][0].y; dh[i][2] = dh2[i][1].x; dh[i][3] = dh2[i][1].y; }
         // ---- matmul 2: dW_hh[g][k] += sum_b dgh[b][g] * h_{t-1}[b][k]   (g = g0.., k = j0..) ----
         if (!DEFER_DW)
 #pragma unroll 2
@@ -331,12 +342,13 @@ __global__ void __launch_bounds__(256, DEFER_DW ? 2 : 1) gru_bwd_kernel(GruBwdAr
                 float4 d = *reinterpret_cast<const float4*>(&Ds[b * D_LD + g0 + q]);
                 dv[q] = d.x; dv[q + 1] = d.y; dv[q + 2] = d.z; dv[q + 3] = d.w;
             }
+            const float2 hpa = make_float2(hp.x, hp.y), hpb = make_float2(hp.z, hp.w);
 #pragma unroll
             for (int q = 0; q < 12; ++q) {
-                dW[q][0] = fmaf(dv[q], hp.x, dW[q][0]);
-                dW[q][1] = fmaf(dv[q], hp.y, dW[q][1]);
-                dW[q][2] = fmaf(dv[q], hp.z, dW[q][2]);
-                dW[q][3] = fmaf(dv[q], hp.w, dW[q][3]);
+                const float2 d2 = make_float2(dv[q], dv[q]);
+                float2 lo = __ffma2_rn(d2, hpa, make_float2(dW[q][0], dW[q][1]));
+                float2 hi = __ffma2_rn(d2, hpb, make_float2(dW[q][2], dW[q][3]));
+                dW[q][0] = lo.x; dW[q][1] = lo.y; dW[q][2] = hi.x; dW[q][3] = hi.y;
             }
         }
         __syncthreads();
