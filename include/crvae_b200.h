@@ -89,8 +89,9 @@ int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const float* w_hi, c
                       const float* b_ih, float* gates, int P, int T, int B, int K, int t_skip, void* stream);
 /* Tensor-core form of crvae_proj_wgrad (3xTF32, MN-major UMMA operands straight from the natural
  * layouts; the gate gradients are split into tf32 hi/lo inside the kernel).  x_hi/x_lo [T,B,K].  */
+size_t crvae_proj_wgrad_tc_workspace(int P, int T, int B, int K, int t_skip);
 int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const float* x_lo, const uint8_t* mask,
-                        float* dw_ih, int P, int T, int B, int K, int t_skip, void* stream);
+                        float* dw_ih, int P, int T, int B, int K, int t_skip, void* workspace, void* stream);
 /* hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i] (exact in fp32)               */
 int crvae_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);
 
@@ -145,13 +146,16 @@ int crvae_gru_bwd(float* gates, const float* ghn, const float* hs,
  * dw_hh is NOT produced and `ghn` is overwritten in place with dgh_n = da_n*r; crvae_gru_dwhh_tc then computes
  *   dw_hh[i][g][k] = sum_{t,b} dgh[i][t][b][g] * h_{t-1}[i][b][k]
  * as one tcgen05 GEMM per head (3xTF32, MN-major operands read in place, tf32 split in shared memory).
- * Needs B % 32 == 0.  Halves the FFMA work of the BPTT kernel and lets two of its CTAs share an SM.            */
+ * Needs B % 32 == 0.  Halves the FFMA work of the BPTT kernel and lets two of its CTAs share an SM.
+ * Both tensor-core gradient GEMMs cut a head's reduction range into several CTAs when a rank holds few heads
+ * (head shards on multi-GPU) and sum the partials in fixed order; `workspace` >= the *_workspace() size.        */
 int crvae_gru_bwd_deferred(float* gates, float* ghn, const float* hs, const float* h0, int64_t h0_head_stride,
                            const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
                            const float* dhs, float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0,
                            int P, int T, int B, void* workspace, void* stream);
+size_t crvae_gru_dwhh_tc_workspace(int P, int T, int B);
 int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const float* hs, const float* h0,
-                      int64_t h0_head_stride, float* dw_hh, int P, int T, int B, void* stream);
+                      int64_t h0_head_stride, float* dw_hh, int P, int T, int B, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused reparameterisation + KL  (CRVAE.forward :210-216, VRAE4E.forward :157-163, trainer :486)

@@ -104,7 +104,8 @@ def test_projection_wgrad_tensor_core_3xtf32(P, T, B, K, t_skip):
     dgc = dg.cuda()
     for m in (None, mask):
         dw = torch.full((P, G, K), 3.0, device="cuda")
-        k.proj_wgrad_tc(dgc, xh, xl, None if m is None else m.cuda(), dw, P, T, B, K, t_skip)
+        ws = torch.zeros(k.proj_wgrad_tc_workspace(P, T, B, K, t_skip) // 4 + 4, device="cuda")
+        k.proj_wgrad_tc(dgc, xh, xl, None if m is None else m.cuda(), dw, P, T, B, K, t_skip, ws)
         torch.cuda.synchronize()
         r = ref if m is None else ref * m[:, None, :].double()
         assert _rel(dw, r) < 2e-5, (_rel(dw, r), P, K)
@@ -207,7 +208,8 @@ def test_gru_backward_deferred_dwhh_tensor_core(P, T, B, lin, shared_h0):
     ws = torch.zeros(k.gru_bwd_workspace(P, B) // 4 + 4, device="cuda")
     k.gru_bwd_deferred(gpu["g"], ghn, c(fw["hs"]), c(h0), stride, c(w_hh), c(w_lin), c(dpred), c(dh_last), c(dhs), gpu["db_hh"],
                        gpu["db_ih"], gpu["dw_lin"], gpu["db_lin"], gpu["dh0"], P, T, B, ws)
-    k.gru_dwhh_tc(gpu["g"], ghn, c(fw["hs"]), c(h0), stride, gpu["dw_hh"], P, T, B)
+    ws2 = torch.zeros(k.gru_dwhh_tc_workspace(P, T, B) // 4 + 4, device="cuda")
+    k.gru_dwhh_tc(gpu["g"], ghn, c(fw["hs"]), c(h0), stride, gpu["dw_hh"], P, T, B, ws2)
     torch.cuda.synchronize()
     for name, v in ref.items():
         if v is not None:

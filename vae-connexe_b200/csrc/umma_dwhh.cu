@@ -19,6 +19,8 @@ namespace crvae {
 
 int make_tmap_generic(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, bool atom32b);
+int tc_splits_for(int P, int tiles_per_head, int nchunks);
+int launch_split_sum(const float* ws, float* out, int P, int S, long long n, cudaStream_t st);
 
 constexpr int DH_H = CRVAE_HIDDEN;
 constexpr int DH_G = CRVAE_G;
@@ -34,9 +36,10 @@ constexpr int DH_TMEM_COLS = 128;
 constexpr int DH_SMEM_BYTES = DH_STAGES * DH_STAGE_BYTES + 1024 + 256;
 
 struct DwhhArgs {
-    float* dw_hh;      // [P][G][H]
+    float* dw_hh;      // [P][G][H]  (splits == 1)  or partials [P][splits][G][H]
     int rows, B;       // rows = T*B
     int h0_per_head;
+    int splits;        // the T*B rows of a head are cut into `splits` contiguous parts (blockIdx.y)
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -52,8 +55,12 @@ gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int head = blockIdx.x;
-    const int nchunks = (a.rows + DH_BK - 1) / DH_BK;
+    const int head = blockIdx.x, split = blockIdx.y;
+    const int nchunks_all = (a.rows + DH_BK - 1) / DH_BK;
+    const int per = (nchunks_all + a.splits - 1) / a.splits;
+    const int c_begin = split * per;
+    const int c_end = (c_begin + per < nchunks_all) ? c_begin + per : nchunks_all;
+    const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmG); prefetch_tmap(&tmN); prefetch_tmap(&tmH); prefetch_tmap(&tmZ); }
     if (warp == 1) {
@@ -76,7 +83,7 @@ gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
                 const int s = c % DH_STAGES, ph = (c / DH_STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = smem + s * DH_STAGE_BYTES;
-                const int m0 = c * DH_BK;
+                const int m0 = (c_begin + c) * DH_BK;
                 mbar_arrive_expect_tx(&full[s], DH_HALF);
                 tma_load_4d(st + DH_OFF_A0, &tmG, &full[s], 0, m0, 0, head);
                 tma_load_4d(st + DH_OFF_A1, &tmN, &full[s], 0, m0, 0, head);
@@ -93,7 +100,7 @@ gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + s * DH_STAGE_BYTES);
                 const uint64_t b_hi = smem_desc_mn_sw128_32b(st + DH_OFF_B, DH_BLOCK), b_lo = smem_desc_mn_sw128_32b(st + DH_HALF + DH_OFF_B, DH_BLOCK);
-                int ksteps = (a.rows - c * DH_BK + 7) / 8;
+                int ksteps = (a.rows - (c_begin + c) * DH_BK + 7) / 8;
                 if (ksteps > DH_BK / 8) ksteps = DH_BK / 8;
 #pragma unroll
                 for (int tile = 0; tile < 2; ++tile) {
@@ -148,7 +155,11 @@ gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tile * DH_H + c0), v);
                 tmem_ld_wait();
                 if (g < DH_G) {
-                    float* dst = a.dw_hh + (static_cast<long long>(head) * DH_G + g) * DH_H + c0;
+                    float* dst = a.dw_hh + ((static_cast<long long>(head) * a.splits + split) * DH_G + g) * DH_H + c0;
+                    if (nchunks == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
@@ -169,8 +180,13 @@ using namespace crvae;
 
 // dgates [P,T,B,G] (dgi, as left by crvae_gru_bwd), dghn [P,T,B,H] (= da_n*r, written by crvae_gru_bwd in defer mode),
 // hs [P,T,B,H], h0 [B,H] (stride 0) or [P,B,H].  Needs B % 32 == 0.
+extern "C" size_t crvae_gru_dwhh_tc_workspace(int P, int T, int B) {
+    const int S = tc_splits_for(P, 1, (T * B + DH_BK - 1) / DH_BK);
+    return S > 1 ? (size_t)P * S * DH_G * DH_H * sizeof(float) : 16;
+}
+
 extern "C" int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const float* hs, const float* h0,
-                                 int64_t h0_head_stride, float* dw_hh, int P, int T, int B, void* stream) {
+                                 int64_t h0_head_stride, float* dw_hh, int P, int T, int B, void* workspace, void* stream) {
     CRVAE_REQUIRE(dgates && dghn && hs && h0 && dw_hh, "null operand");
     CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0 && B % 32 == 0, "bad size (B must be a multiple of 32)");
     CRVAE_REQUIRE(aligned16(dgates) && aligned16(dghn) && aligned16(hs) && aligned16(h0) && aligned16(dw_hh), "16-byte alignment");
@@ -204,7 +220,11 @@ extern "C" int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const f
         if (e != cudaSuccess) { set_error("gru_dwhh_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    DwhhArgs a{dw_hh, (int)TB, B, h0_head_stride != 0};
-    gru_dwhh_tc_kernel<<<P, 192, DH_SMEM_BYTES, (cudaStream_t)stream>>>(tG, tN, tH, tZ, a);
-    return check_launch("gru_dwhh_tc_kernel");
+    const int S = tc_splits_for(P, 1, ((int)TB + DH_BK - 1) / DH_BK);
+    if (S > 1) CRVAE_REQUIRE(workspace && aligned16(workspace), "workspace required (crvae_gru_dwhh_tc_workspace)");
+    DwhhArgs a{S > 1 ? (float*)workspace : dw_hh, (int)TB, B, h0_head_stride != 0, S};
+    gru_dwhh_tc_kernel<<<dim3(P, S), 192, DH_SMEM_BYTES, (cudaStream_t)stream>>>(tG, tN, tH, tZ, a);
+    rc = check_launch("gru_dwhh_tc_kernel");
+    if (rc || S == 1) return rc;
+    return launch_split_sum((const float*)workspace, dw_hh, P, S, (long long)DH_G * DH_H, (cudaStream_t)stream);
 }

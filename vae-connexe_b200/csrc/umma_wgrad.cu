@@ -39,9 +39,10 @@ constexpr int WG_TMEM_COLS = 256;
 constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 
 struct WgradTcArgs {
-    float* dW;               // [P][G][K]
+    float* dW;               // [P][G][K]  (splits == 1)  or partials [P][splits][G][K]
     const uint8_t* mask;     // [P][K] or null
     int K, R, row_off;       // R = rows reduced per head (starting at row_off within the head's T*B rows)
+    int splits;              // the reduction range of a head is cut into `splits` contiguous parts (blockIdx.z)
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -57,8 +58,12 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k_tile = blockIdx.x, head = blockIdx.y;
-    const int nchunks = (a.R + WG_BK - 1) / WG_BK;
+    const int k_tile = blockIdx.x, head = blockIdx.y, split = blockIdx.z;
+    const int nchunks_all = (a.R + WG_BK - 1) / WG_BK;
+    const int per = (nchunks_all + a.splits - 1) / a.splits;
+    const int c_begin = split * per;
+    const int c_end = (c_begin + per < nchunks_all) ? c_begin + per : nchunks_all;
+    const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmX_hi); prefetch_tmap(&tmX_lo); prefetch_tmap(&tmG); }
     if (warp == 1) {
@@ -81,7 +86,7 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
                 const int s = c % WG_STAGES, ph = (c / WG_STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = smem + s * WG_STAGE_BYTES;
-                const int row = a.row_off + c * WG_BK;
+                const int row = a.row_off + (c_begin + c) * WG_BK;
                 mbar_arrive_expect_tx(&full[s], WG_TX_BYTES);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -102,7 +107,7 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
                 const uint64_t a_hi = smem_desc_mn_sw128_32b(st, WG_BLOCK_BYTES), a_lo = smem_desc_mn_sw128_32b(st + WG_A_BYTES, WG_BLOCK_BYTES);
                 const uint64_t b_hi = smem_desc_mn_sw128_32b(st + 2 * WG_A_BYTES, WG_BLOCK_BYTES);
                 const uint64_t b_lo = smem_desc_mn_sw128_32b(st + 2 * WG_A_BYTES + WG_B_BYTES, WG_BLOCK_BYTES);
-                int ksteps = (a.R - c * WG_BK + 7) / 8;
+                int ksteps = (a.R - (c_begin + c) * WG_BK + 7) / 8;
                 if (ksteps > WG_BK / 8) ksteps = WG_BK / 8;
                 for (int k = 0; k < ksteps; ++k) {
                     const uint64_t adv = static_cast<uint64_t>(k * (1024 >> 4));   // next 8 reduction rows = next 1024-byte atom
@@ -112,7 +117,7 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
                 }
                 mma_commit(&empty[s]);
             }
-            mma_commit(tmem_full);
+            mma_commit(tmem_full);               // (also fires when this split had no chunks)
         }
     } else {
         const int cw = warp - 2;                     // converter warp 0..3
@@ -144,7 +149,7 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
         tc_fence_after();
         float mval = 1.f;
         if (a.mask && kcol < a.K) mval = a.mask[static_cast<long long>(head) * a.K + kcol] ? 1.f : 0.f;
-        float* out = a.dW + static_cast<long long>(head) * WG_BN * a.K + kcol;
+        float* out = a.dW + (static_cast<long long>(head) * a.splits + split) * WG_BN * a.K + kcol;
 #pragma unroll 1
         for (int c0 = 0; c0 < WG_BN; c0 += 32) {
             float v[32];
@@ -152,7 +157,7 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
             tmem_ld_wait();
             if (kcol < a.K) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) out[static_cast<long long>(c0 + j) * a.K] = v[j] * mval;
+                for (int j = 0; j < 32; ++j) out[static_cast<long long>(c0 + j) * a.K] = nchunks > 0 ? v[j] * mval : 0.f;
             }
         }
         tc_fence_before();
@@ -168,8 +173,42 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
 
 using namespace crvae;
 
+namespace crvae {
+// sum the per-split partials in fixed order: out[p][e] = sum_s ws[p][s][e]
+__global__ void split_sum_kernel(const float* __restrict__ ws, float* __restrict__ out, int S, long long n) {
+    const long long p = blockIdx.y;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += ws[(p * S + s) * n + e];
+        out[p * n + e] = acc;
+    }
+}
+
+int tc_splits_for(int P, int tiles_per_head, int nchunks) {
+    // one CTA per (tile, head) leaves SMs idle when a rank holds few heads: cut the reduction so the grid approaches
+    // the SM count without spilling into a second wave
+    int s = 148 / (P * tiles_per_head);
+    if (s < 1) s = 1;
+    if (s > nchunks) s = nchunks;
+    if (s > 16) s = 16;
+    return s;
+}
+int launch_split_sum(const float* ws, float* out, int P, int S, long long n, cudaStream_t st) {
+    int bx = (int)((n + 255) / 256);
+    if (bx > 64) bx = 64;
+    split_sum_kernel<<<dim3(bx, P), 256, 0, st>>>(ws, out, S, n);
+    return check_launch("split_sum_kernel");
+}
+}  // namespace crvae
+
+extern "C" size_t crvae_proj_wgrad_tc_workspace(int P, int T, int B, int K, int t_skip) {
+    const int R = (T - t_skip) * B;
+    const int S = tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK);
+    return S > 1 ? (size_t)P * S * CRVAE_G * K * sizeof(float) : 16;
+}
+
 extern "C" int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const float* x_lo, const uint8_t* mask,
-                                   float* dw_ih, int P, int T, int B, int K, int t_skip, void* stream) {
+                                   float* dw_ih, int P, int T, int B, int K, int t_skip, void* workspace, void* stream) {
     CRVAE_REQUIRE(dgates && x_hi && x_lo && dw_ih, "null operand");
     CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0 && K > 0 && t_skip >= 0 && t_skip <= T, "bad size");
     CRVAE_REQUIRE(K % 4 == 0, "tensor-core weight gradient needs K % 4 == 0 (16-byte TMA row pitch); use crvae_proj_wgrad");
@@ -192,8 +231,12 @@ extern "C" int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const
         if (e != cudaSuccess) { set_error("proj_wgrad_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    WgradTcArgs a{dw_ih, mask, K, R, t_skip * B};
-    dim3 grid((K + WG_BM - 1) / WG_BM, P);
+    const int S = tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK);
+    if (S > 1) CRVAE_REQUIRE(workspace && aligned16(workspace), "workspace required (crvae_proj_wgrad_tc_workspace)");
+    WgradTcArgs a{S > 1 ? (float*)workspace : dw_ih, mask, K, R, t_skip * B, S};
+    dim3 grid((K + WG_BM - 1) / WG_BM, P, S);
     proj_wgrad_tc_kernel<<<grid, 192, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tX_hi, tX_lo, tG, a);
-    return check_launch("proj_wgrad_tc_kernel");
+    rc = check_launch("proj_wgrad_tc_kernel");
+    if (rc || S == 1) return rc;
+    return launch_split_sum((const float*)workspace, dw_ih, P, S, (long long)CRVAE_G * K, (cudaStream_t)stream);
 }

@@ -169,6 +169,10 @@ class CRVAEEngine:
                      k.proj_wgrad_workspace(1, ENC_STEPS, B, self.p))
         self.ws_wgrad = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)
         self.ws_wgrad_dec = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)   # side-stream twin
+        self.ws_wgrad_tc = self.ws_dwhh = None
+        if hasattr(k, "proj_wgrad_tc_workspace") and P > 0:     # split-reduction partials of the tensor-core gradient GEMMs
+            self.ws_wgrad_tc = torch.zeros(k.proj_wgrad_tc_workspace(P, DEC_STEPS, B, self.p, 1) // 4 + 4, dtype=torch.float32, device=dev)
+            self.ws_dwhh = torch.zeros(k.gru_dwhh_tc_workspace(P, DEC_STEPS, B) // 4 + 4, dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------ forward
     def forward(self, eps: Optional[torch.Tensor] = None, want_err: bool = False):
@@ -297,9 +301,10 @@ class CRVAEEngine:
             k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
         if P > 0:
             if defer:
-                k.gru_dwhh_tc(self.gates, self.ghn, self.hs, self.zlat, 0, g["w_hh"], P, DEC_STEPS, B)
+                k.gru_dwhh_tc(self.gates, self.ghn, self.hs, self.zlat, 0, g["w_hh"], P, DEC_STEPS, B, self.ws_dwhh)
             if self.proj_mode == "tc3":
-                k.proj_wgrad_tc(self.gates, self.dec_in_hi, self.dec_in_lo, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1)
+                k.proj_wgrad_tc(self.gates, self.dec_in_hi, self.dec_in_lo, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1,
+                                self.ws_wgrad_tc)
             else:
                 k.proj_wgrad(self.gates, self.dec_in, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1, self.ws_wgrad_dec)
             if lam_ridge != 0.0:      # d/dW of lam*(|linear.W|^2 + |W_hh|^2), ridge_regularize :321-325

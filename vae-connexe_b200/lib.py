@@ -26,7 +26,8 @@ SIGNATURES = {
                                 _c_i64, _c_void_p, _c_int, _c_i64, _c_void_p, _c_i64, _c_int, _c_void_p]),
     "crvae_proj_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p]),
     "crvae_proj_fwd_tc": (_c_int, [_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p]),
-    "crvae_proj_wgrad_tc": (_c_int, [_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p]),
+    "crvae_proj_wgrad_tc_workspace": (_c_size_t, [_c_int] * 5),
+    "crvae_proj_wgrad_tc": (_c_int, [_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
     "crvae_split_tf32": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_void_p]),
     "crvae_proj_wgrad_workspace": (_c_size_t, [_c_int] * 4),
     "crvae_proj_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
@@ -35,7 +36,8 @@ SIGNATURES = {
     "crvae_gru_bwd_workspace": (_c_size_t, [_c_int] * 2),
     "crvae_gru_bwd": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 11 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
     "crvae_gru_bwd_deferred": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 10 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
-    "crvae_gru_dwhh_tc": (_c_int, [_c_void_p] * 4 + [_c_i64, _c_void_p] + [_c_int] * 3 + [_c_void_p]),
+    "crvae_gru_dwhh_tc_workspace": (_c_size_t, [_c_int] * 3),
+    "crvae_gru_dwhh_tc": (_c_int, [_c_void_p] * 4 + [_c_i64, _c_void_p] + [_c_int] * 3 + [_c_void_p, _c_void_p]),
     "crvae_latent_fwd": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_int, _c_void_p]),
     "crvae_latent_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_void_p,
                                   _c_void_p, _c_int, _c_int, _c_void_p]),
@@ -142,9 +144,12 @@ class Kernels:
         self._ck(self.lib.crvae_proj_fwd_tc(ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(b_ih), ptr(gates), P, T, B, K,
                                             t_skip, stream_ptr()), "crvae_proj_fwd_tc")
 
-    def proj_wgrad_tc(self, dgates, x_hi, x_lo, mask, dw_ih, P, T, B, K, t_skip):
+    def proj_wgrad_tc_workspace(self, P, T, B, K, t_skip) -> int:
+        return int(self.lib.crvae_proj_wgrad_tc_workspace(P, T, B, K, t_skip))
+
+    def proj_wgrad_tc(self, dgates, x_hi, x_lo, mask, dw_ih, P, T, B, K, t_skip, ws=None):
         self._ck(self.lib.crvae_proj_wgrad_tc(ptr(dgates), ptr(x_hi), ptr(x_lo), ptr(mask), ptr(dw_ih), P, T, B, K, t_skip,
-                                              stream_ptr()), "crvae_proj_wgrad_tc")
+                                              ptr(ws), stream_ptr()), "crvae_proj_wgrad_tc")
 
     def split_tf32(self, src, hi, lo, n):
         self._ck(self.lib.crvae_split_tf32(ptr(src), ptr(hi), ptr(lo), n, stream_ptr()), "crvae_split_tf32")
@@ -181,9 +186,12 @@ class Kernels:
                                                  ptr(dpred), ptr(dh_last), ptr(dhs), ptr(db_hh), ptr(db_ih), ptr(dw_lin),
                                                  ptr(db_lin), ptr(dh0), P, T, B, ptr(ws), stream_ptr()), "crvae_gru_bwd_deferred")
 
-    def gru_dwhh_tc(self, dgates, dghn, hs, h0, h0_stride, dw_hh, P, T, B):
+    def gru_dwhh_tc_workspace(self, P, T, B) -> int:
+        return int(self.lib.crvae_gru_dwhh_tc_workspace(P, T, B))
+
+    def gru_dwhh_tc(self, dgates, dghn, hs, h0, h0_stride, dw_hh, P, T, B, ws=None):
         self._ck(self.lib.crvae_gru_dwhh_tc(ptr(dgates), ptr(dghn), ptr(hs), ptr(h0), h0_stride, ptr(dw_hh), P, T, B,
-                                            stream_ptr()), "crvae_gru_dwhh_tc")
+                                            ptr(ws), stream_ptr()), "crvae_gru_dwhh_tc")
 
     def latent_fwd(self, lat, eps, z, kl_out, B, kl_form, Z=64):
         self._ck(self.lib.crvae_latent_fwd(ptr(lat), ptr(eps), ptr(z), ptr(kl_out), B, Z, kl_form, stream_ptr()),
