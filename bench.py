@@ -306,6 +306,12 @@ def run_ours(args):
         "gd_prox_gc": ("hbm", 12.0 * P_loc * G * K),
     }
     roof_all = {}
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")     # ncu dram bytes per launch (same config only)
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("p") == p_total and tj.get("B") == B and world == 1:
+            traffic = tj
     for tag, (bound, amount) in alg.items():
         if tag not in stages: continue
         dur = stages[tag]["ms_per_step"] * 1e-3
@@ -313,7 +319,8 @@ def run_ours(args):
             ach, peak, unit = amount / dur / 1e9, pk["hbm"], "GB/s"
         else:   # no fp32 tensor mode exists; TF32 dense peak = half the measured bf16 burst
             ach, peak, unit = amount / dur / 1e12, pk["bf16"] / 2.0, "TFLOP/s"
-        roof_all[tag] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "ms": dur * 1e3, "traffic": None}
+        roof_all[tag] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "ms": dur * 1e3, "traffic": traffic.get(tag),
+                         "algorithmic": amount}
     total_stage_ms = sum(v["ms_per_step"] for v in stages.values())
     dom = max((t for t in roof_all), key=lambda t: roof_all[t]["ms"]) if roof_all else None
     roofline = dict(roof_all[dom], kernel=dom, share_of_step=roof_all[dom]["ms"] / total_stage_ms, peak_source=pk["source"]) if dom else None

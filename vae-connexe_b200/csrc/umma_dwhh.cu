@@ -19,13 +19,13 @@ namespace crvae {
 
 int make_tmap_generic(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, bool atom32b);
-int tc_splits_for(int P, int tiles_per_head, int nchunks);
+int tc_splits_for(int P, int tiles_per_head, int nchunks, int ctas_per_sm);
 int launch_split_sum(const float* ws, float* out, int P, int S, long long n, cudaStream_t st);
 
 constexpr int DH_H = CRVAE_HIDDEN;
 constexpr int DH_G = CRVAE_G;
-constexpr int DH_BK = 32;                          // reduction rows per stage (16 x 6 stages measured slower: 125 vs 110 us)
-constexpr int DH_STAGES = 3;
+constexpr int DH_BK = 16;                          // reduction rows per stage
+constexpr int DH_STAGES = 3;                       // 3 x 32 KB: two CTAs share an SM
 constexpr int DH_BLOCK = DH_BK * 128;              // 4096 B: one MN-block (32 elements wide) of a stage = LBO
 constexpr int DH_OFF_A0 = 0;                       // 4 blocks: g 0..127
 constexpr int DH_OFF_A1 = 4 * DH_BLOCK;            // 2 blocks: g 128..191
@@ -42,7 +42,7 @@ struct DwhhArgs {
     int splits;        // the T*B rows of a head are cut into `splits` contiguous parts (blockIdx.y)
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmN,
                    const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmZ, DwhhArgs a) {
     using namespace umma;
@@ -181,7 +181,7 @@ using namespace crvae;
 // dgates [P,T,B,G] (dgi, as left by crvae_gru_bwd), dghn [P,T,B,H] (= da_n*r, written by crvae_gru_bwd in defer mode),
 // hs [P,T,B,H], h0 [B,H] (stride 0) or [P,B,H].  Needs B % 32 == 0.
 extern "C" size_t crvae_gru_dwhh_tc_workspace(int P, int T, int B) {
-    const int S = tc_splits_for(P, 1, (T * B + DH_BK - 1) / DH_BK);
+    const int S = tc_splits_for(P, 1, (T * B + DH_BK - 1) / DH_BK, 2);
     return S > 1 ? (size_t)P * S * DH_G * DH_H * sizeof(float) : 16;
 }
 
@@ -220,7 +220,7 @@ extern "C" int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const f
         if (e != cudaSuccess) { set_error("gru_dwhh_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    const int S = tc_splits_for(P, 1, ((int)TB + DH_BK - 1) / DH_BK);
+    const int S = tc_splits_for(P, 1, ((int)TB + DH_BK - 1) / DH_BK, 2);
     if (S > 1) CRVAE_REQUIRE(workspace && aligned16(workspace), "workspace required (crvae_gru_dwhh_tc_workspace)");
     DwhhArgs a{S > 1 ? (float*)workspace : dw_hh, (int)TB, B, h0_head_stride != 0, S};
     gru_dwhh_tc_kernel<<<dim3(P, S), 192, DH_SMEM_BYTES, (cudaStream_t)stream>>>(tG, tN, tH, tZ, a);

@@ -29,7 +29,7 @@ int make_tmap_generic(CUtensorMap* m, const float* base, int rank, const uint64_
 constexpr int WG_BM = 128;                 // input columns k per tile (UMMA M, TMEM lanes)
 constexpr int WG_BN = CRVAE_G;             // 192 gate rows (UMMA N, TMEM columns)
 constexpr int WG_BK = 16;                  // reduction rows (m) per stage (more, smaller stages: deeper TMA pipeline)
-constexpr int WG_STAGES = 4;
+constexpr int WG_STAGES = 4;                // (2 stages + two CTAs per SM measured slower: 111 vs 93 us)
 constexpr int WG_A_BYTES = WG_BM * WG_BK * 4;          // 4 MN-blocks x [WG_BK rows x 128 B]
 constexpr int WG_B_BYTES = WG_BN * WG_BK * 4;          // 6 MN-blocks x [WG_BK rows x 128 B]
 constexpr int WG_BLOCK_BYTES = WG_BK * 128;            // 4096: one MN-block (32 M/N elements) of a stage = LBO
@@ -184,10 +184,10 @@ __global__ void split_sum_kernel(const float* __restrict__ ws, float* __restrict
     }
 }
 
-int tc_splits_for(int P, int tiles_per_head, int nchunks) {
+int tc_splits_for(int P, int tiles_per_head, int nchunks, int ctas_per_sm) {
     // one CTA per (tile, head) leaves SMs idle when a rank holds few heads: cut the reduction so the grid approaches
     // the SM count without spilling into a second wave
-    int s = 148 / (P * tiles_per_head);
+    int s = (148 * ctas_per_sm) / (P * tiles_per_head);
     if (s < 1) s = 1;
     if (s > nchunks) s = nchunks;
     if (s > 16) s = 16;
@@ -203,7 +203,7 @@ int launch_split_sum(const float* ws, float* out, int P, int S, long long n, cud
 
 extern "C" size_t crvae_proj_wgrad_tc_workspace(int P, int T, int B, int K, int t_skip) {
     const int R = (T - t_skip) * B;
-    const int S = tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK);
+    const int S = tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK, 1);
     return S > 1 ? (size_t)P * S * CRVAE_G * K * sizeof(float) : 16;
 }
 
@@ -231,7 +231,7 @@ extern "C" int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const
         if (e != cudaSuccess) { set_error("proj_wgrad_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    const int S = tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK);
+    const int S = tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK, 1);
     if (S > 1) CRVAE_REQUIRE(workspace && aligned16(workspace), "workspace required (crvae_proj_wgrad_tc_workspace)");
     WgradTcArgs a{S > 1 ? (float*)workspace : dw_ih, mask, K, R, t_skip * B, S};
     dim3 grid((K + WG_BM - 1) / WG_BM, P, S);
