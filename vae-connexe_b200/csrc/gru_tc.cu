@@ -1,17 +1,18 @@
 // Persistent multi-head GRU recurrence, FORWARD, on the 5th-generation tensor cores (tcgen05).
 //
-// One CTA owns one head and up to TWO 128-row batch tiles for ALL timesteps:
-//   * W_hh of the head (tf32 hi and lo parts, 2 x 48 KB) is brought in ONCE by TMA and stays in
-//     shared memory (K-major, SWIZZLE_128B);
-//   * per step and tile ONE thread issues the gate GEMM  gh[128 x 192] = h[128 x 64] . W_hh^T  as
-//     8 K-steps x 3 tcgen05.mma (3xTF32: h_lo.W_hi + h_hi.W_lo + h_hi.W_hi, fp32 accumulate in TMEM);
-//   * a warpgroup per tile (thread = batch row, hidden state kept in 64 registers) reads the accumulator
-//     with tcgen05.ld, streams gi from global, does the r/z/n gate math, the per-head Linear(H,1),
-//     writes r|z|n, gh_n, h back (row-contiguous float4) and re-writes the tile's h as tf32 hi/lo
-//     directly in the swizzled K-major operand layout (conflict-free 16-byte stores), then signals
-//     the issuer through an mbarrier (fence.proxy.async);
-//   * the two tiles ping-pong: while one warpgroup does its pointwise math the tensor core works on
-//     the other tile.
+// One CTA owns one (head, 128-row batch tile) pair for ALL timesteps:
+//   * W_hh of the head (tf32 hi and lo parts, 2 x 48 KB) is brought in ONCE by TMA and stays in shared
+//     memory (K-major, SWIZZLE_128B) as the B operand;
+//   * the hidden state is the A operand and lives in TENSOR MEMORY (tf32 hi | lo, 2 x 64 columns): the
+//     pointwise threads write h_t there with tcgen05.st, no shared-memory round trip, no swizzle;
+//   * per step ONE thread issues the gate GEMM  gh[128 x 192] = h[128 x 64] . W_hh^T  as 8 K-steps x 3
+//     tcgen05.mma (3xTF32: h_lo.W_hi + h_hi.W_lo + h_hi.W_hi, fp32 accumulate in TMEM);
+//   * 16 warps do the gate math on 16x256b TMEM fragments (warp = lane quadrant x 16-column group): a
+//     thread owns 4 batch rows x 4 hidden units for the whole sequence, so h stays in 16 registers, and
+//     every global access is a float2 whose quad covers one full 32-byte sector (8 sectors per request,
+//     all bytes used) in the row-major activation layout -- no staging buffer needed;
+//   * gi of step t+1 does not depend on the recurrence: its 24 float2 loads per thread are issued before
+//     the step barrier, so ~96 KB of loads per SM are in flight while the tensor core runs step t+1.
 // Same buffers / semantics as gru_fwd_kernel (gru_recurrent.cu), which remains the exact-fp32 path.
 //
 // Reference arithmetic replaced: nn.GRU per-step linear_hh + cell (CRVAE_lorenz96.py:119) and
@@ -21,25 +22,20 @@
 
 namespace crvae {
 
-int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
-                 uint32_t box_inner, uint32_t box_rows, bool atom32b);
-
 constexpr int GH = CRVAE_HIDDEN;                 // 64
 constexpr int GG = CRVAE_G;                      // 192
 constexpr int GT_ROWS = 128;                     // rows per tile (UMMA M)
 constexpr int GT_W_HALF = GG * 128;              // 24576 B: [192 rows x 32 k] fp32, one K half
 constexpr int GT_W_BYTES = 2 * GT_W_HALF;        // 49152 B per (hi | lo)
-constexpr int GT_H_HALF = GT_ROWS * 128;         // 16384 B: [128 rows x 32 k]
-constexpr int GT_H_BYTES = 2 * GT_H_HALF;        // 32768 B per (hi | lo) per tile
 constexpr int GT_OFF_WHI = 0;
 constexpr int GT_OFF_WLO = GT_W_BYTES;
-constexpr int GT_OFF_H = 2 * GT_W_BYTES;         // tile s: + s * 2 * GT_H_BYTES ; hi then lo
-constexpr int GT_OFF_CONST = GT_OFF_H + 4 * GT_H_BYTES;          // b_hh[192] | b_ih[192] | w_lin[64] | b_lin
-constexpr int GT_CONST_BYTES = (2 * GG + GH + 4) * 4;
-constexpr int GT_OFF_BAR = GT_OFF_CONST + ((GT_CONST_BYTES + 15) / 16) * 16;
-constexpr int GT_SMEM_BYTES = GT_OFF_BAR + 128 + 1024;
+constexpr int GT_OFF_PRED = 2 * GT_W_BYTES;                      // [2 parities][128 rows][2 column groups] (+ slack)
+constexpr int GT_OFF_CONST = GT_OFF_PRED + 2 * GT_ROWS * 4 * 4;  // b_ih[192] | b_hh[192]
+constexpr int GT_OFF_BAR = GT_OFF_CONST + (2 * GG + GH) * 4;          // ... | w_lin[64]
+constexpr int GT_SMEM_BYTES = GT_OFF_BAR + 64 + 1024;
 constexpr int GT_TMEM_COLS = 512;
-constexpr int GT_THREADS = 32 + 256;             // warp 0: TMA + MMA issue; warps 1-4: tile 0; warps 5-8: tile 1
+constexpr int GT_ACOL_HI = 0, GT_ACOL_LO = GH, GT_DCOL = 2 * GH;  // TMEM columns: h_hi | h_lo | gh[192]
+constexpr int GT_THREADS = 512;
 
 struct GruTcArgs {
     float* gates; const float* b_ih; const float* b_hh;
@@ -49,16 +45,26 @@ struct GruTcArgs {
     int P, T, B, t_skip;
 };
 
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
+// 16 lanes x 32 columns fragment: thread (tr = lane/4, tq = lane%4) register 4*i + 2*rr + e  <->
+// TMEM lane (base + tr + 8*rr), column (col + 8*i + 2*tq + e)
+__device__ __forceinline__ void tmem_ld_16x32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_16x32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float tf32_rna(float v) {
     uint32_t t;
@@ -66,200 +72,240 @@ __device__ __forceinline__ float tf32_rna(float v) {
     return __uint_as_float(t);
 }
 
-// one 16-byte chunk (4 consecutive k) of row `row` of a K-major SWIZZLE_128B tile pair (hi | lo)
-__device__ __forceinline__ void store_h_chunk(uint8_t* h_hi_s, uint8_t* h_lo_s, int row, int c, float v0, float v1, float v2,
-                                              float v3) {
-    const float a0 = tf32_rna(v0), a1 = tf32_rna(v1), a2 = tf32_rna(v2), a3 = tf32_rna(v3);
-    const int half = c >> 3, cc = c & 7;
-    const int off = half * GT_H_HALF + row * 128 + ((cc ^ (row & 7)) << 4);
-    *reinterpret_cast<float4*>(h_hi_s + off) = make_float4(a0, a1, a2, a3);
-    *reinterpret_cast<float4*>(h_lo_s + off) = make_float4(__fsub_rn(v0, a0), __fsub_rn(v1, a1), __fsub_rn(v2, a2), __fsub_rn(v3, a3));
+// 256-bit global accesses (sm_100+): 8 consecutive floats of one row per thread, so the 4 threads of a quad
+// cover one full 128-byte line -> a warp request touches 8 lines instead of 8 x (bytes / 32)
+__device__ __forceinline__ void ldg_v8_stream(const float* p, float* v) {
+    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(float* p, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4),
+                 "f"(v5), "f"(v6), "f"(v7)
+                 : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem], issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+        : "memory");
+}
+
+// Column permutation inside every 32-block of hidden units.  A thread's 16x256b fragment holds the TMEM columns
+// p = 8i + 2tq + e (i < 4, e < 2); storing hidden unit u = 8tq + 2i + e at position p makes those 8 values
+// 8 CONSECUTIVE units, i.e. one 32-byte vector of the row-major activations.  The same permutation is applied
+// to the K index (columns of the h operand / of W_hh) and to the N index (gate rows of W_hh), so the GEMM
+// is unchanged: gh[:, p] = sum_p' h[:, u(p')] * W_hh[u(p), u(p')].
+__device__ __forceinline__ int pos_of_unit(int u) { return (u & ~31) | (((u >> 1) & 3) << 3) | (((u >> 3) & 3) << 1) | (u & 1); }
+
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, GruTcArgs a) {
+gru_fwd_tc_kernel(GruTcArgs a, const float* __restrict__ w_hi, const float* __restrict__ w_lo) {
     using namespace umma;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    float* cst = reinterpret_cast<float*>(smem + GT_OFF_CONST);      // b_hh | b_ih | w_lin | b_lin
-    uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);
-    uint64_t* hbar = wbar + 1;        // [2] h tile written (4 warp arrivals)
-    uint64_t* mbar = hbar + 2;        // [2] accumulator complete (tcgen05.commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset form keeps the shared address space (LDS/STS, not generic LD/ST)
+    float* pred_s = reinterpret_cast<float*>(smem + GT_OFF_PRED);
+    float* bih_s = reinterpret_cast<float*>(smem + GT_OFF_CONST);
+    float* bhh_s = bih_s + GG;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);      // accumulator complete (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
-    const int b_base = blockIdx.x * 2 * GT_ROWS;
-    const int ntiles = (a.B - b_base > GT_ROWS) ? 2 : 1;
+    const int b_base = blockIdx.x * GT_ROWS;
+    const int q = warp & 3, hh = (warp >> 2) & 1, cg = warp >> 3;   // TMEM lane quadrant, 16-lane half, 32-column group
+    const int tr = lane >> 2, tq = lane & 3;
+    const bool has_lin = a.w_lin != nullptr;
 
-    // constants of this head -> smem
-    for (int e = threadIdx.x; e < 2 * GG + GH + 1; e += GT_THREADS) {
-        float v;
-        if (e < GG) v = __ldg(a.b_hh + (long long)head * GG + e);
-        else if (e < 2 * GG) v = __ldg(a.b_ih + (long long)head * GG + (e - GG));
-        else if (e < 2 * GG + GH) v = a.w_lin ? __ldg(a.w_lin + (long long)head * GH + (e - 2 * GG)) : 0.f;
-        else v = a.b_lin ? __ldg(a.b_lin + head) : 0.f;
-        cst[e] = v;
-    }
+    for (int e = threadIdx.x; e < 2 * GG + GH; e += GT_THREADS)
+        bih_s[e] = e < GG       ? __ldg(a.b_ih + (long long)head * GG + e)
+                   : e < 2 * GG ? __ldg(a.b_hh + (long long)head * GG + (e - GG))
+                                : (has_lin ? __ldg(a.w_lin + (long long)head * GH + (e - 2 * GG)) : 0.f);
     if (warp == 0) {
         if (lane == 0) {
-            prefetch_tmap(&tmW_hi); prefetch_tmap(&tmW_lo);
-            mbar_init(wbar, 1);
-            for (int s = 0; s < 2; ++s) { mbar_init(&hbar[s], 4); mbar_init(&mbar[s], 1); }
+            mbar_init(mbar, 1);
             fence_barrier_init();
         }
         __syncwarp();
         tmem_alloc<GT_TMEM_COLS>(tmem_slot);
+    }
+    // W_hh hi / lo of this head -> shared memory B operand (K-major, SWIZZLE_128B), rows and columns permuted
+    {
+        const float4* src_hi = reinterpret_cast<const float4*>(w_hi + (long long)head * GG * GH);
+        const float4* src_lo = reinterpret_cast<const float4*>(w_lo + (long long)head * GG * GH);
+        for (int idx = threadIdx.x; idx < GG * (GH / 4); idx += GT_THREADS) {
+            const int r = idx >> 4, c4 = idx & 15;                       // source gate row, 4-unit chunk
+            const int n = (r / GH) * GH + pos_of_unit(r % GH);           // destination row
+            const int kp = pos_of_unit(4 * c4);                          // units 4c4, 4c4+1 -> kp, kp+1 ; 4c4+2, 4c4+3 -> kp+8, kp+9
+            const int half = kp >> 5, k0 = kp & 31, k1 = k0 + 8;
+            const uint32_t rowoff = half * GT_W_HALF + n * 128;
+            const uint32_t o0 = rowoff + ((((k0 >> 2) ^ (n & 7)) << 4) | ((k0 & 3) << 2));
+            const uint32_t o1 = rowoff + ((((k1 >> 2) ^ (n & 7)) << 4) | ((k1 & 3) << 2));
+            const float4 vh = __ldg(src_hi + idx), vl = __ldg(src_lo + idx);
+            *reinterpret_cast<float2*>(smem + GT_OFF_WHI + o0) = make_float2(vh.x, vh.y);
+            *reinterpret_cast<float2*>(smem + GT_OFF_WHI + o1) = make_float2(vh.z, vh.w);
+            *reinterpret_cast<float2*>(smem + GT_OFF_WLO + o0) = make_float2(vl.x, vl.y);
+            *reinterpret_cast<float2*>(smem + GT_OFF_WLO + o1) = make_float2(vl.z, vl.w);
+        }
+        fence_proxy_async_smem();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            // W_hh hi / lo of this head: two K halves each, once
-            mbar_arrive_expect_tx(wbar, 2 * GT_W_BYTES);
-            tma_load_2d(smem + GT_OFF_WHI, &tmW_hi, wbar, 0, head * GG);
-            tma_load_2d(smem + GT_OFF_WHI + GT_W_HALF, &tmW_hi, wbar, 32, head * GG);
-            tma_load_2d(smem + GT_OFF_WLO, &tmW_lo, wbar, 0, head * GG);
-            tma_load_2d(smem + GT_OFF_WLO + GT_W_HALF, &tmW_lo, wbar, 32, head * GG);
-            mbar_wait(wbar, 0);
-            constexpr uint32_t idesc = idesc_tf32(GT_ROWS, GG, false, false);
-            const uint32_t w_hi = smem_u32(smem + GT_OFF_WHI), w_lo = smem_u32(smem + GT_OFF_WLO);
-            for (int t = 0; t < a.T; ++t) {
-                for (int s = 0; s < ntiles; ++s) {
-                    mbar_wait(&hbar[s], t & 1);           // h_{t-1} of tile s is in smem, accumulator s has been drained
-                    tc_fence_after();
-                    const uint32_t h_hi = smem_u32(smem + GT_OFF_H + s * 2 * GT_H_BYTES), h_lo = h_hi + GT_H_BYTES;
-                    const uint32_t acc = tmem_base + static_cast<uint32_t>(s * GG);
+    // this thread's elements: batch rows brow0 + 8rr, hidden units ucol + m (m < 8);  fragment register
+    // k = 4(m >> 1) + 2rr + (m & 1)
+    const int ucol = 32 * cg + 8 * tq;
+    const int brow0 = b_base + 32 * q + 16 * hh + tr;
+    const float* wl = bih_s + 2 * GG + ucol;
+    const float blin = (has_lin && a.b_lin) ? __ldg(a.b_lin + head) : 0.f;
+
+    float h[16], gi[3][16];
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * q + 16 * hh) << 16) + static_cast<uint32_t>(32 * cg);
+
+    auto load_gi = [&](int t) {
+        if (t < a.t_skip) {
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint32_t offA = (kk >> 2) * GT_H_HALF + (kk & 3) * 32;
-                        const uint32_t offB = (kk >> 2) * GT_W_HALF + (kk & 3) * 32;
-                        mma_tf32_ss(acc, smem_desc_k_sw128(h_lo + offA), smem_desc_k_sw128(w_hi + offB), idesc, kk != 0);
-                        mma_tf32_ss(acc, smem_desc_k_sw128(h_hi + offA), smem_desc_k_sw128(w_lo + offB), idesc, true);
-                        mma_tf32_ss(acc, smem_desc_k_sw128(h_hi + offA), smem_desc_k_sw128(w_hi + offB), idesc, true);
-                    }
-                    mma_commit(&mbar[s]);
-                }
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int k = 0; k < 16; ++k) gi[g][k] = bih_s[g * GH + ucol + 2 * (k >> 2) + (k & 1)];
+            return;
+        }
+        const float* gbase = a.gates + ((long long)head * a.T + t) * a.B * GG + ucol;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int b = brow0 + 8 * rr;
+            const float* grow = gbase + (long long)b * GG;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (b < a.B) ldg_v8_stream(grow + g * GH, v);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) gi[g][4 * (m >> 1) + 2 * rr + (m & 1)] = v[m];
             }
         }
-    } else {
-        const int s = (warp - 1) >> 2;                     // tile of this warpgroup
-        if (s < ntiles) {
-            const int q = warp & 3;                        // TMEM lane quadrant accessible to this warp
-            const int row = q * 32 + lane;                 // row inside the tile == TMEM lane
-            const int gb = b_base + s * GT_ROWS + row;     // batch row
-            const bool live = gb < a.B;
-            const bool has_lin = a.w_lin != nullptr;
-            uint8_t* h_hi_s = smem + GT_OFF_H + s * 2 * GT_H_BYTES;
-            uint8_t* h_lo_s = h_hi_s + GT_H_BYTES;
-            const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(s * GG);
-            const float* bhh = cst;
-            const float* bih = cst + GG;
-            const float* wl = cst + 2 * GG;
-
-            // h0 -> registers + operand tile
-            float h[GH];
-            {
-                const float* h0 = a.h0 + (long long)head * a.h0_stride + (long long)gb * GH;
+    };
+    auto store_h_operand = [&]() {     // h (registers) -> TMEM A operand, tf32 hi | lo
+        float hi[16], lo[16];
 #pragma unroll
-                for (int c = 0; c < GH / 4; ++c) {
-                    float4 v = live ? __ldg(reinterpret_cast<const float4*>(h0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    h[4 * c] = v.x; h[4 * c + 1] = v.y; h[4 * c + 2] = v.z; h[4 * c + 3] = v.w;
-                }
+        for (int k = 0; k < 16; ++k) {
+            hi[k] = tf32_rna(h[k]);
+            lo[k] = __fsub_rn(h[k], hi[k]);
+        }
+        tmem_st_16x32(lane_addr + GT_ACOL_HI, hi);
+        tmem_st_16x32(lane_addr + GT_ACOL_LO, lo);
+        tmem_st_wait();
+    };
+    auto issue_step = [&]() {          // thread 0: the 24 MMAs of one step
+        tc_fence_after();
+        constexpr uint32_t idesc = idesc_tf32(GT_ROWS, GG, false, false);
+        const uint32_t w_hi_s = smem_u32(smem + GT_OFF_WHI), w_lo_s = smem_u32(smem + GT_OFF_WLO);
+        const uint32_t acc = tmem_base + GT_DCOL;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t offB = (kk >> 2) * GT_W_HALF + (kk & 3) * 32;
+            const uint32_t a_hi = tmem_base + GT_ACOL_HI + kk * 8, a_lo = tmem_base + GT_ACOL_LO + kk * 8;
+            mma_tf32_ts(acc, a_lo, smem_desc_k_sw128(w_hi_s + offB), idesc, kk != 0);
+            mma_tf32_ts(acc, a_hi, smem_desc_k_sw128(w_lo_s + offB), idesc, true);
+            mma_tf32_ts(acc, a_hi, smem_desc_k_sw128(w_hi_s + offB), idesc, true);
+        }
+        mma_commit(mbar);
+    };
+
+    // h0 -> registers -> operand
+    {
+        const float* h0 = a.h0 + (long long)head * a.h0_stride + ucol;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int b = brow0 + 8 * rr;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (b < a.B) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(h0 + (long long)b * GH));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(h0 + (long long)b * GH) + 1);
+                v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
             }
 #pragma unroll
-            for (int c = 0; c < 16; ++c) store_h_chunk(h_hi_s, h_lo_s, row, c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hbar[s]);
-
-            for (int t = 0; t < a.T; ++t) {
-                const long long grow = ((long long)head * a.T + t) * a.B + gb;      // global row of (head, t, b)
-                float* gdst = a.gates + grow * GG;
-                const bool use_bias = t < a.t_skip;
-                mbar_wait(&mbar[s], t & 1);
-                tc_fence_after();
-                float ps = 0.f;
-#pragma unroll
-                for (int jc = 0; jc < GH; jc += 16) {      // fully unrolled: h[] stays in registers
-                    // gate by gate to bound register pressure: r, then z, then n / h'
-                    float acc_v[16], gi_v[16], rr[16], zz[16];
-                    auto load_gi = [&](int gate) {
-                        if (live && !use_bias) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                float4 v = *reinterpret_cast<const float4*>(gdst + gate * GH + jc + 4 * c);
-                                gi_v[4 * c] = v.x; gi_v[4 * c + 1] = v.y; gi_v[4 * c + 2] = v.z; gi_v[4 * c + 3] = v.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) gi_v[e] = bih[gate * GH + jc + e];
-                        }
-                    };
-                    tmem_ld_32x16(acc + jc, acc_v);
-                    load_gi(0);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) rr[e] = sigmoidf_fast(gi_v[e] + (acc_v[e] + bhh[jc + e]));
-                    tmem_ld_32x16(acc + GH + jc, acc_v);
-                    load_gi(1);
-                    if (live) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<float4*>(gdst + jc + 4 * c) = make_float4(rr[4 * c], rr[4 * c + 1], rr[4 * c + 2], rr[4 * c + 3]);
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) zz[e] = sigmoidf_fast(gi_v[e] + (acc_v[e] + bhh[GH + jc + e]));
-                    tmem_ld_32x16(acc + 2 * GH + jc, acc_v);
-                    load_gi(2);
-                    if (live) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<float4*>(gdst + GH + jc + 4 * c) = make_float4(zz[4 * c], zz[4 * c + 1], zz[4 * c + 2], zz[4 * c + 3]);
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const float ghn_ = acc_v[e] + bhh[2 * GH + jc + e];
-                        const float n = tanhf_fast(__fadd_rn(gi_v[e], __fmul_rn(rr[e], ghn_)));
-                        const float hn = __fadd_rn(__fmul_rn(__fsub_rn(h[jc + e], n), zz[e]), n);
-                        h[jc + e] = hn;
-                        acc_v[e] = ghn_;      // reuse: gh_n
-                        gi_v[e] = n;          // reuse: n
-                        ps = fmaf(hn, wl[jc + e], ps);
-                    }
-                    if (live) {
-                        float* gh_dst = a.ghn + grow * GH + jc;
-                        float* hs_dst = a.hs + grow * GH + jc;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            *reinterpret_cast<float4*>(gdst + 2 * GH + jc + 4 * c) = make_float4(gi_v[4 * c], gi_v[4 * c + 1], gi_v[4 * c + 2], gi_v[4 * c + 3]);
-                            *reinterpret_cast<float4*>(gh_dst + 4 * c) = make_float4(acc_v[4 * c], acc_v[4 * c + 1], acc_v[4 * c + 2], acc_v[4 * c + 3]);
-                            *reinterpret_cast<float4*>(hs_dst + 4 * c) = make_float4(h[jc + 4 * c], h[jc + 4 * c + 1], h[jc + 4 * c + 2], h[jc + 4 * c + 3]);
-                        }
-                    }
-                    if (t + 1 < a.T) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            store_h_chunk(h_hi_s, h_lo_s, row, (jc >> 2) + c, h[jc + 4 * c], h[jc + 4 * c + 1], h[jc + 4 * c + 2],
-                                          h[jc + 4 * c + 3]);
-                    }
-                }
-                if (live && has_lin) a.pred[grow] = ps + cst[2 * GG + GH];
-                if (t + 1 < a.T) {
-                    tc_fence_before();                 // accumulator reads of this step are complete
-                    fence_proxy_async_smem();          // h tile (generic-proxy stores) visible to the tensor core
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&hbar[s]);
-                }
-            }
-            tc_fence_before();
+            for (int m = 0; m < 8; ++m) h[4 * (m >> 1) + 2 * rr + (m & 1)] = v[m];
         }
     }
+    store_h_operand();
+    load_gi(0);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) issue_step();
+
+    for (int t = 0; t < a.T; ++t) {
+        const long long trow = ((long long)head * a.T + t) * a.B;       // global row of (head, t, b = 0)
+        mbar_wait(mbar, t & 1);
+        tc_fence_after();
+        float* pred_t = pred_s + (t & 1) * GT_ROWS * 2;
+        {
+            float ar[16], az[16];
+            tmem_ld_16x32(lane_addr + GT_DCOL, ar);
+            tmem_ld_16x32(lane_addr + GT_DCOL + GH, az);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {                 // r, z replace gi_r, gi_z
+                const int m = 2 * (k >> 2) + (k & 1);      // unit offset of register k
+                gi[0][k] = sigmoidf_fast(gi[0][k] + (ar[k] + bhh_s[ucol + m]));
+                gi[1][k] = sigmoidf_fast(gi[1][k] + (az[k] + bhh_s[GH + ucol + m]));
+            }
+            tmem_ld_16x32(lane_addr + GT_DCOL + 2 * GH, ar);
+            tmem_ld_wait();
+            float ps[2] = {0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {                 // gh_n replaces the accumulator, n replaces gi_n
+                const int m = 2 * (k >> 2) + (k & 1);
+                const float ghn_ = ar[k] + bhh_s[2 * GH + ucol + m];
+                const float n = tanhf_fast(__fadd_rn(gi[2][k], __fmul_rn(gi[0][k], ghn_)));
+                const float hn = __fadd_rn(__fmul_rn(__fsub_rn(h[k], n), gi[1][k]), n);
+                h[k] = hn;
+                ar[k] = ghn_;
+                gi[2][k] = n;
+                ps[(k >> 1) & 1] = fmaf(hn, wl[m], ps[(k >> 1) & 1]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int b = brow0 + 8 * rr;
+                if (b < a.B) {
+                    const long long grow = trow + b;
+                    float* gdst = a.gates + grow * GG + ucol;
+                    const int k0 = 2 * rr;      // register of unit m: k0 + 4(m >> 1) + (m & 1)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g)
+                        stg_v8(gdst + g * GH, gi[g][k0], gi[g][k0 + 1], gi[g][k0 + 4], gi[g][k0 + 5], gi[g][k0 + 8], gi[g][k0 + 9],
+                               gi[g][k0 + 12], gi[g][k0 + 13]);
+                    stg_v8(a.ghn + grow * GH + ucol, ar[k0], ar[k0 + 1], ar[k0 + 4], ar[k0 + 5], ar[k0 + 8], ar[k0 + 9], ar[k0 + 12],
+                           ar[k0 + 13]);
+                    stg_v8(a.hs + grow * GH + ucol, h[k0], h[k0 + 1], h[k0 + 4], h[k0 + 5], h[k0 + 8], h[k0 + 9], h[k0 + 12], h[k0 + 13]);
+                }
+                if (has_lin) {
+                    float p = ps[rr];
+                    p += __shfl_xor_sync(0xffffffffu, p, 1);
+                    p += __shfl_xor_sync(0xffffffffu, p, 2);
+                    if (tq == 0) pred_t[(32 * q + 16 * hh + tr + 8 * rr) * 2 + cg] = p;
+                }
+            }
+        }
+        if (t + 1 < a.T) {
+            store_h_operand();
+            load_gi(t + 1);            // in flight across the barrier and the next gate GEMM
+        }
+        tc_fence_before();             // accumulator reads / operand writes of this step are complete
+        __syncthreads();
+        if (threadIdx.x == 0 && t + 1 < a.T) issue_step();
+        if (has_lin && threadIdx.x < GT_ROWS && b_base + threadIdx.x < a.B) {
+            const float2 p2 = *reinterpret_cast<const float2*>(pred_t + threadIdx.x * 2);
+            a.pred[trow + b_base + threadIdx.x] = (p2.x + p2.y) + blin;
+        }
+    }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
@@ -282,11 +328,11 @@ extern "C" int crvae_gru_fwd_tc(float* gates, const float* b_ih, const float* w_
     CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0 && t_skip >= 0 && t_skip <= T, "bad size");
     CRVAE_REQUIRE(aligned16(gates) && aligned16(hs) && aligned16(ghn) && aligned16(h0) && aligned16(w_hh_hi) && aligned16(w_hh_lo),
                   "16-byte alignment");
+    CRVAE_REQUIRE(h0_head_stride % 4 == 0, "h0 head stride must keep 16-byte alignment");
+    CRVAE_REQUIRE((reinterpret_cast<uintptr_t>(gates) & 31u) == 0 && (reinterpret_cast<uintptr_t>(hs) & 31u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(ghn) & 31u) == 0,
+                  "32-byte alignment of the activation buffers");
     if (P == 0) return 0;
-    CUtensorMap tW_hi, tW_lo;
-    int rc;
-    if ((rc = make_tmap_2d(&tW_hi, w_hh_hi, GH, (uint64_t)P * GG, GH, 32, GG, false))) return rc;
-    if ((rc = make_tmap_2d(&tW_lo, w_hh_lo, GH, (uint64_t)P * GG, GH, 32, GG, false))) return rc;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES);
@@ -294,7 +340,7 @@ extern "C" int crvae_gru_fwd_tc(float* gates, const float* b_ih, const float* w_
         attr_done = true;
     }
     GruTcArgs a{gates, b_ih, b_hh, h0, (long long)h0_head_stride, w_lin, b_lin, hs, ghn, pred, P, T, B, t_skip};
-    dim3 grid((B + 2 * GT_ROWS - 1) / (2 * GT_ROWS), P);
-    gru_fwd_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, (cudaStream_t)stream>>>(tW_hi, tW_lo, a);
+    dim3 grid((B + GT_ROWS - 1) / GT_ROWS, P);
+    gru_fwd_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, (cudaStream_t)stream>>>(a, w_hh_hi, w_hh_lo);
     return check_launch("gru_fwd_tc_kernel");
 }

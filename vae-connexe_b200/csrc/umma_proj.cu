@@ -46,7 +46,7 @@ proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, ProjTcArgs a) {
     using namespace umma;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset form keeps the shared address space (LDS/STS, not generic LD/ST)
     float* slabs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_SLAB_BYTES);
     uint64_t* empty = full + TC_STAGES;

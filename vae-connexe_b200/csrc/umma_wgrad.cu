@@ -50,7 +50,7 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
                      const __grid_constant__ CUtensorMap tmG, WgradTcArgs a) {
     using namespace umma;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset form keeps the shared address space (LDS/STS, not generic LD/ST)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
     uint64_t* conv = full + WG_STAGES;
     uint64_t* empty = conv + WG_STAGES;
