@@ -119,8 +119,10 @@ int crvae_gru_fwd(float* gates, const float* b_ih, const float* w_hh, const floa
                   int P, int T, int B, int t_skip, void* stream);
 
 /* Tensor-core form of crvae_gru_fwd (same buffers and results to fp32 rounding): the per-step gate
- * GEMM h.W_hh^T runs on tcgen05 (3xTF32, accumulator in TMEM), W_hh (hi/lo from crvae_split_tf32,
- * [P,G,H] each) stays resident in shared memory for all timesteps.                                  */
+ * GEMM h.W_hh^T runs on tcgen05 (3xTF32; h operand and accumulator in TMEM), W_hh stays resident in
+ * shared memory for all timesteps.  w_hh_hi / w_hh_lo = crvae_split_tf32(W_hh) ([P,G,H] each), or
+ * w_hh_hi = the fp32 W_hh itself and w_hh_lo = NULL (split while staging).  gates / hs / ghn must be
+ * 32-byte aligned (256-bit vector accesses).                                                       */
 int crvae_gru_fwd_tc(float* gates, const float* b_ih, const float* w_hh_hi, const float* w_hh_lo,
                      const float* b_hh, const float* h0, int64_t h0_head_stride,
                      const float* w_lin, const float* b_lin, float* hs, float* ghn, float* pred,
@@ -153,6 +155,16 @@ int crvae_gru_bwd_deferred(float* gates, float* ghn, const float* hs, const floa
                            const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
                            const float* dhs, float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0,
                            int P, int T, int B, void* workspace, void* stream);
+
+/* Tensor-core form of crvae_gru_bwd_deferred without the dhs input (same buffers, results to fp32 rounding):
+ * the per-step product dh_{t-1} = dh_t*z + dgh.W_hh runs on tcgen05 (3xTF32; dgh operand and accumulator in
+ * TMEM, W_hh resident in shared memory), r|z|n tiles arrive by TMA, column sums are register accumulators.
+ * One CTA per (head, 128-row tile).  gates / ghn / hs / h0 / dh0 / dh_last must be 32-byte aligned.
+ * Replaces autograd through nn.GRU + nn.Linear(H,1) (CRVAE_lorenz96.py:497).                                  */
+int crvae_gru_bwd_tc(float* gates, float* ghn, const float* hs, const float* h0, int64_t h0_head_stride,
+                     const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
+                     float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0, int P, int T, int B,
+                     void* workspace, void* stream);
 size_t crvae_gru_dwhh_tc_workspace(int P, int T, int B);
 int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const float* hs, const float* h0,
                       int64_t h0_head_stride, float* dw_hh, int P, int T, int B, void* workspace, void* stream);

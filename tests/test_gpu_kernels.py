@@ -181,6 +181,44 @@ def test_gru_forward_tensor_core(P, T, B, lin, t_skip, shared_h0):
         assert _rel(out[name], ref[name]) < 2e-5, (name, _rel(out[name], ref[name]))
 
 
+@pytest.mark.parametrize("P,T,B,lin,shared_h0,last", [(3, 10, 256, True, True, False), (2, 5, 64, False, False, True),
+                                                       (20, 10, 256, True, True, False), (1, 10, 32, True, True, True),
+                                                       (2, 3, 300, True, False, True), (1, 1, 128, True, True, False)])
+def test_gru_backward_tensor_core(P, T, B, lin, shared_h0, last):
+    """tcgen05 BPTT (crvae_gru_bwd_tc: dgh operand in TMEM, 3xTF32) + crvae_gru_dwhh_tc against the CPU oracle."""
+    k, o = _k(), OracleKernels()
+    gi = _rand(P, T, B, G, seed=1)
+    b_ih, w_hh, b_hh = _rand(P, G, seed=2, scale=0.2), _rand(P, G, H, seed=3, scale=0.125), _rand(P, G, seed=4, scale=0.2)
+    h0 = _rand(B, H, seed=5) if shared_h0 else _rand(P, B, H, seed=5)
+    stride = 0 if shared_h0 else B * H
+    w_lin, b_lin = (_rand(P, H, seed=6, scale=0.2), _rand(P, seed=7)) if lin else (None, None)
+    c = lambda t: None if t is None else t.cuda()
+    fw = dict(g=gi.clone(), hs=torch.zeros(P, T, B, H), ghn=torch.zeros(P, T, B, H), pred=torch.zeros(P, T, B) if lin else None)
+    o.gru_fwd(fw["g"], b_ih, w_hh, b_hh, h0, stride, w_lin, b_lin, fw["hs"], fw["ghn"], fw["pred"], P, T, B, 0)
+    dpred = _rand(P, T, B, seed=8) if lin else None
+    dh_last = _rand(P, B, H, seed=9, scale=0.1) if last else None
+    z = lambda *s: torch.zeros(*s)
+    ref = dict(g=fw["g"].clone(), dw_hh=z(P, G, H), db_hh=z(P, G), db_ih=z(P, G), dw_lin=z(P, H) if lin else None,
+               db_lin=z(P) if lin else None, dh0=z(P, B, H))
+    o.gru_bwd(ref["g"], fw["ghn"], fw["hs"], h0, stride, w_hh, w_lin, dpred, dh_last, None, ref["dw_hh"], ref["db_hh"], ref["db_ih"],
+              ref["dw_lin"], ref["db_lin"], ref["dh0"], P, T, B, None)
+    gpu = {n: (None if v is None else torch.zeros_like(v).cuda()) for n, v in ref.items()}
+    gpu["g"] = fw["g"].clone().cuda()
+    ghn = fw["ghn"].clone().cuda()
+    ws = torch.zeros(k.gru_bwd_workspace(P, B) // 4 + 4, device="cuda")
+    k.gru_bwd_tc(gpu["g"], ghn, c(fw["hs"]), c(h0), stride, c(w_hh), c(w_lin), c(dpred), c(dh_last), gpu["db_hh"], gpu["db_ih"],
+                 gpu["dw_lin"], gpu["db_lin"], gpu["dh0"], P, T, B, ws)
+    torch.cuda.synchronize()
+    for name in ("g", "db_hh", "db_ih", "dw_lin", "db_lin", "dh0"):
+        if ref[name] is not None:
+            assert _rel(gpu[name], ref[name]) < 5e-5, (name, _rel(gpu[name], ref[name]))
+    if B % 32 == 0:
+        ws2 = torch.zeros(k.gru_dwhh_tc_workspace(P, T, B) // 4 + 4, device="cuda")
+        k.gru_dwhh_tc(gpu["g"], ghn, c(fw["hs"]), c(h0), stride, gpu["dw_hh"], P, T, B, ws2)
+        torch.cuda.synchronize()
+        assert _rel(gpu["dw_hh"], ref["dw_hh"]) < 5e-5
+
+
 @pytest.mark.parametrize("P,T,B,lin,shared_h0", [(3, 10, 256, True, True), (2, 5, 64, False, False), (20, 10, 256, True, True),
                                                   (1, 10, 32, True, True)])
 def test_gru_backward_deferred_dwhh_tensor_core(P, T, B, lin, shared_h0):

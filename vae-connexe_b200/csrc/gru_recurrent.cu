@@ -456,6 +456,13 @@ static int launch_bwd(const GruBwdArgs& a, cudaStream_t st) {
     return check_launch("gru_bwd_kernel");
 }
 
+// used by the tensor-core BPTT (gru_tc_bwd.cu), which writes the same per-tile partial layout (without dW_hh)
+int launch_gru_bwd_finalize(const float* ws, float* db_hh, float* db_ih, float* dw_lin, float* db_lin, int P, int ntiles, cudaStream_t st) {
+    GruFinArgs f{ws, nullptr, db_hh, db_ih, dw_lin, db_lin, ntiles};
+    gru_bwd_finalize_kernel<<<dim3((WS_DBLIN + 256) / 256, P), 256, 0, st>>>(f);
+    return check_launch("gru_bwd_finalize_kernel");
+}
+
 }  // namespace crvae
 
 using namespace crvae;

@@ -92,13 +92,10 @@ class CRVAEEngine:
             zl = lambda t: torch.zeros_like(t)
             self.w_ih_hi, self.w_ih_lo = zl(self.theta["w_ih"]), zl(self.theta["w_ih"])
             self.enc_w_hi, self.enc_w_lo = zl(self.theta["enc_w_ih"]), zl(self.theta["enc_w_ih"])
-        # recurrence mode: "exact" = persistent fp32 FFMA kernel (default); "tc3" = tcgen05 gate GEMM
-        # (crvae_gru_fwd_tc: parity-green, but with row-major activations its lane-per-row global I/O is
-        # uncoalesced and it is slower than the FFMA kernel -- see profiles/r01_ncu_summary.md; opt-in)
+        # recurrence mode: "tc3" = tcgen05 gate GEMM (crvae_gru_fwd_tc, 3xTF32; default once a rank holds enough heads
+        # to fill the SMs with 128-row tiles), "exact" = persistent fp32 FFMA kernel (CRVAE_REC_MODE=exact, small shards)
         import os as _os
-        self.rec_mode = "tc3" if (_os.environ.get("CRVAE_REC_MODE") == "tc3" and hasattr(self.k, "gru_fwd_tc") and P >= 8) else "exact"
-        if self.rec_mode == "tc3":
-            self.w_hh_hi, self.w_hh_lo = torch.zeros_like(self.theta["w_hh"]), torch.zeros_like(self.theta["w_hh"])
+        self.rec_mode = "tc3" if (_os.environ.get("CRVAE_REC_MODE", "tc3") == "tc3" and hasattr(self.k, "gru_fwd_tc") and P >= 8) else "exact"
         self.B = None
         self.kl_form = L.KL_SWAPPED
         self._side = None
@@ -200,8 +197,7 @@ class CRVAEEngine:
         # decoder heads (:218-219 -> GRU.forward :114-121): recurrence (+Linear), MSE
         if P > 0:
             if self.rec_mode == "tc3":
-                k.split_tf32(th["w_hh"], self.w_hh_hi, self.w_hh_lo, P * G * H)
-                k.gru_fwd_tc(self.gates, th["b_ih"], self.w_hh_hi, self.w_hh_lo, th["b_hh"], self.zlat, 0, th["w_lin"],
+                k.gru_fwd_tc(self.gates, th["b_ih"], th["w_hh"], None, th["b_hh"], self.zlat, 0, th["w_lin"],
                              th["b_lin"], self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
             else:
                 k.gru_fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
@@ -270,7 +266,10 @@ class CRVAEEngine:
         # decoder BPTT.  With enough heads the dW_hh accumulation is deferred to one tcgen05 GEMM per head
         # (crvae_gru_dwhh_tc, issued below next to the projection weight gradient): half the FFMA work, 2 CTAs per SM.
         defer = P >= 8 and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
-        if P > 0 and defer:
+        if P > 0 and defer and self.rec_mode == "tc3" and hasattr(k, "gru_bwd_tc"):
+            k.gru_bwd_tc(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None,
+                         g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
+        elif P > 0 and defer:
             k.gru_bwd_deferred(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
                                g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
         elif P > 0:
