@@ -173,7 +173,7 @@ def profile_stages(run, eps_list, reps):
     eng, k = run.eng, run.eng.k
     names, evs = [], []
     orig = {}
-    stage_fns = ["proj_fwd", "proj_fwd_tc", "split_tf32", "proj_wgrad_tc", "gru_fwd_tc", "gru_bwd_deferred", "gru_dwhh_tc", "gru_fwd", "gemm", "latent_fwd", "mse_fwd_bwd", "dot_small", "gru_bwd", "proj_wgrad", "latent_bwd",
+    stage_fns = ["proj_fwd", "proj_fwd_tc", "split_tf32", "proj_wgrad_tc", "gru_fwd_tc", "gru_bwd_deferred", "gru_bwd_tc", "gru_dwhh_tc", "gru_fwd", "gemm", "latent_fwd", "mse_fwd_bwd", "dot_small", "gru_bwd", "proj_wgrad", "latent_bwd",
                  "gd_prox_gc", "gd_step", "axpy"]
     records = []
 
@@ -184,8 +184,8 @@ def profile_stages(run, eps_list, reps):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(); fn(*a, **kw); e.record()
             tag = name
-            if name in ("proj_fwd", "gru_fwd", "gru_bwd", "proj_wgrad", "proj_fwd_tc", "proj_wgrad_tc", "gru_fwd_tc", "gru_bwd_deferred", "gru_dwhh_tc"):
-                P = {"proj_fwd": 4, "gru_fwd": 11, "gru_bwd": 16, "proj_wgrad": 4, "proj_fwd_tc": 6, "proj_wgrad_tc": 5, "gru_fwd_tc": 12, "gru_bwd_deferred": 15, "gru_dwhh_tc": 6}[name]
+            if name in ("proj_fwd", "gru_fwd", "gru_bwd", "proj_wgrad", "proj_fwd_tc", "proj_wgrad_tc", "gru_fwd_tc", "gru_bwd_deferred", "gru_bwd_tc", "gru_dwhh_tc"):
+                P = {"proj_fwd": 4, "gru_fwd": 11, "gru_bwd": 16, "proj_wgrad": 4, "proj_fwd_tc": 6, "proj_wgrad_tc": 5, "gru_fwd_tc": 12, "gru_bwd_deferred": 15, "gru_bwd_tc": 14, "gru_dwhh_tc": 6}[name]
                 P = a[P]
                 tag = f"{name}[{'dec' if P == eng.P and eng.P != 1 else 'enc' if P == 1 else 'dec'}]"
             records.append((tag, s, e))
@@ -300,7 +300,7 @@ def run_ours(args):
     units_loc = B * TD * P_loc
     # algorithmic HBM bytes / flops per launch (DESIGN.md "Kernels")
     alg = {
-        "gru_bwd[dec]": ("hbm", 1796.0 * units_loc), "gru_bwd_deferred[dec]": ("hbm", 1796.0 * units_loc), "gru_fwd[dec]": ("hbm", 1028.0 * units_loc), "gru_fwd_tc[dec]": ("hbm", 1028.0 * units_loc),
+        "gru_bwd[dec]": ("hbm", 1796.0 * units_loc), "gru_bwd_deferred[dec]": ("hbm", 1796.0 * units_loc), "gru_bwd_tc[dec]": ("hbm", 1796.0 * units_loc), "gru_fwd[dec]": ("hbm", 1028.0 * units_loc), "gru_fwd_tc[dec]": ("hbm", 1028.0 * units_loc),
         "proj_fwd[dec]": ("tensor", 2.0 * K * G * 0.9 * units_loc), "proj_wgrad[dec]": ("tensor", 2.0 * K * G * 0.9 * units_loc),
         "proj_fwd_tc[dec]": ("tensor", 2.0 * K * G * 0.9 * units_loc), "proj_wgrad_tc[dec]": ("tensor", 2.0 * K * G * 0.9 * units_loc),
         "gd_prox_gc": ("hbm", 12.0 * P_loc * G * K),

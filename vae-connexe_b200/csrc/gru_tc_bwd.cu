@@ -139,21 +139,18 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gru_bwd_tc_kernel(const __grid_
     for (int m = 0; m < 8; ++m) wl[m] = wl_s[ucol + m];
 
     float pf_ghn[4][8], pf_hp[4][8], dp_cur[4], dp_prev[4];     // slot s = 2hh + rr
-    auto prefetch = [&](int t) {                   // gh_n[t], h_{t-1}, dpred[t-1] of this thread's rows
+    auto prefetch_slot = [&](int t, int s) {       // gh_n[t], h_{t-1}, dpred[t-1] of row slot s
+        const int b = b_base + lrow0 + 16 * (s >> 1) + 8 * (s & 1);
+        if (b < a.B) {
+            const long long grow = head_row0 + (long long)t * a.B + b;
+            ldg_v8_stream(a.ghn + grow * BH + ucol, pf_ghn[s]);
+            if (t > 0) ldg_v8(a.hs + (grow - a.B) * BH + ucol, pf_hp[s]);
+            else       ldg_v8(h0 + (long long)b * BH, pf_hp[s]);
+            dp_prev[s] = (has_lin && t > 0) ? __ldg(a.dpred + grow - a.B) : 0.f;
+        } else {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int b = b_base + lrow0 + 16 * (s >> 1) + 8 * (s & 1);
-            if (b < a.B) {
-                const long long grow = head_row0 + (long long)t * a.B + b;
-                ldg_v8_stream(a.ghn + grow * BH + ucol, pf_ghn[s]);
-                if (t > 0) ldg_v8(a.hs + (grow - a.B) * BH + ucol, pf_hp[s]);
-                else       ldg_v8(h0 + (long long)b * BH, pf_hp[s]);
-                dp_prev[s] = (has_lin && t > 0) ? __ldg(a.dpred + grow - a.B) : 0.f;
-            } else {
-#pragma unroll
-                for (int m = 0; m < 8; ++m) { pf_ghn[s][m] = 0.f; pf_hp[s][m] = 0.f; }
-                dp_prev[s] = 0.f;
-            }
+            for (int m = 0; m < 8; ++m) { pf_ghn[s][m] = 0.f; pf_hp[s][m] = 0.f; }
+            dp_prev[s] = 0.f;
         }
     };
     // dw_lin needs h_t (the OUTPUT of step t) while the loop only ever loads h_{t-1}: fold in h_{T-1} here
@@ -170,7 +167,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gru_bwd_tc_kernel(const __grid_
             for (int m = 0; m < 8; ++m) acc[32 + m] = fmaf(dp_cur[s], hv[m], acc[32 + m]);
         }
     }
-    prefetch(a.T - 1);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) prefetch_slot(a.T - 1, s);
 
     auto issue_step = [&]() {          // thread 0: the 72 MMAs of one step (accumulate onto the pre-loaded dh*z)
         tc_fence_after();
@@ -234,7 +232,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gru_bwd_tc_kernel(const __grid_
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
                     const int k = 4 * (m >> 1) + 2 * rr + (m & 1);
-                    const float r = live ? rv[m] : 0.f, z = live ? zv[m] : 0.f, n = live ? nv[m] : 0.f;
+                    const float r = rv[m], z = zv[m], n = nv[m];     // dead rows: d == 0 and the tile holds finite values -> all products 0
                     const float d = fmaf(dp, wl[m], dh[k]);              // total dL/dh_t
                     const float dn = d * (1.f - z);
                     const float dz = d * (pf_hp[s][m] - n);
@@ -249,6 +247,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gru_bwd_tc_kernel(const __grid_
                     acc[32 + m] = fmaf(dpm1, pf_hp[s][m], acc[32 + m]);
                 }
                 if (tq == 0 && cg == 0) acc[40] += dp;
+                dp_cur[s] = dpm1;
+                // the inputs of step t-1 go into the load queue AHEAD of this step's stores (their registers are free now)
+                if (t > 0) prefetch_slot(t - 1, s);
                 if (live) {
                     const long long grow = head_row0 + (long long)t * a.B + b;
                     float* gdst = a.gates + grow * BG + ucol;
@@ -257,7 +258,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gru_bwd_tc_kernel(const __grid_
                     stg_v8(gdst + 2 * BH, o_n[0], o_n[1], o_n[2], o_n[3], o_n[4], o_n[5], o_n[6], o_n[7]);
                     stg_v8(a.ghn + grow * BH + ucol, o_g[0], o_g[1], o_g[2], o_g[3], o_g[4], o_g[5], o_g[6], o_g[7]);
                 }
-                dp_cur[s] = dpm1;
             }
             // A operand (tf32 hi | lo) and the dh * z pre-load of the accumulator
             const uint32_t la = lane_addr + (static_cast<uint32_t>(16 * hh) << 16);
@@ -278,7 +278,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) gru_bwd_tc_kernel(const __grid_
                 tmem_st_16x32(la + BT_ACOL_LO + 2 * BH, lo);
             }
         }
-        if (t > 0) prefetch(t - 1);          // in flight across the barrier and the next GEMM
         tmem_st_wait();
         tc_fence_before();                   // operand / accumulator writes and gate-tile reads of this step are complete
         __syncthreads();
