@@ -83,8 +83,10 @@ int crvae_proj_fwd(const float* x, const float* w_ih, const float* b_ih, float* 
 
 /* Tensor-core form of crvae_proj_fwd: tcgen05.mma kind::tf32 fed by TMA, accumulators in TMEM,
  * error-compensated 3xTF32 (A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi, fp32 accumulate) so the result agrees
- * with the fp32 reference to ~1e-6 relative.  Operands arrive pre-split (crvae_split_tf32):
- * x_hi/x_lo [T,B,K], w_hi/w_lo [P,G,K].  Needs K % 4 == 0 (TMA row pitch).                    */
+ * with the fp32 reference to ~1e-6 relative.  Operands arrive pre-split: x_hi/x_lo [T,B,K] from
+ * crvae_split_tf32, w_hi/w_lo [P,G,K] from crvae_split_tf32_gate_rows (gate rows permuted inside
+ * every 32-block so that the epilogue's TMEM fragments store 256-bit row segments directly).
+ * Needs K % 4 == 0 (TMA row pitch); gates 32-byte aligned.                                      */
 int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
                       const float* b_ih, float* gates, int P, int T, int B, int K, int t_skip, void* stream);
 /* Tensor-core form of crvae_proj_wgrad (3xTF32, MN-major UMMA operands straight from the natural
@@ -94,6 +96,10 @@ int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const float* x_l
                         float* dw_ih, int P, int T, int B, int K, int t_skip, void* workspace, void* stream);
 /* hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i] (exact in fp32)               */
 int crvae_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);
+/* Same split of a [rows, cols] matrix with row r written to row (r & ~31) | perm(r & 31), where
+ * perm(u) = 8*((u>>1)&3) + 2*(u>>3) + (u&1): the operand layout crvae_proj_fwd_tc expects for W_ih.
+ * rows % 32 == 0; not in place.                                                                 */
+int crvae_split_tf32_gate_rows(const float* src, float* hi, float* lo, int64_t rows, int cols, void* stream);
 
 /* Weight gradient of the projection (autograd of the above, :497):
  *   dw_ih[i] (G x K) = sum_{t>=t_skip,b} dgates[i][t][b][:]^T x[t][b][:]   (x mask[i][k] if mask)

@@ -77,7 +77,11 @@ def test_projection_tensor_core_3xtf32(P, T, B, K, t_skip):
     ref = (torch.einsum("tbk,pgk->ptbg", x.double(), w.double()) + b.double()[:, None, None, :])
     xc, wc = x.cuda(), w.cuda()
     xh, xl, wh, wl = (torch.empty_like(t) for t in (xc, xc, wc, wc))
-    k.split_tf32(xc, xh, xl, xc.numel()); k.split_tf32(wc, wh, wl, wc.numel())
+    k.split_tf32(xc, xh, xl, xc.numel()); k.split_tf32_gate_rows(wc, wh, wl, P * G, K)
+    u = torch.arange(32)
+    perm = (8 * ((u >> 1) & 3) + 2 * (u >> 3) + (u & 1))                    # row r of W lands at (r & ~31) | perm[r & 31]
+    dst = ((torch.arange(P * G) & ~31) | perm[torch.arange(P * G) & 31]).cuda()
+    assert torch.equal((wh + wl).view(P * G, K)[dst], wc.view(P * G, K))
     assert torch.equal(xh + xl, xc) and float((xh.view(torch.int32) & 0x1FFF).abs().sum()) == 0     # exact split, hi is tf32
     g = torch.full((P, T, B, G), 7.0, device="cuda")
     k.proj_fwd_tc(xh, xl, wh, wl, b.cuda(), g, P, T, B, K, t_skip)

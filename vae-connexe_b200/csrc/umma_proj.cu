@@ -14,8 +14,7 @@
 // smem ring: 2 stages x 80 KB, full/empty mbarriers; TWO accumulators of 128 lanes x 192 fp32 columns in TMEM
 // (tmem_full / tmem_empty mbarriers) so the epilogue of one tile overlaps the MMAs of the next.
 #include <stdlib.h>
-#include "common.cuh"
-#include "umma.cuh"
+#include "gru_tc_common.cuh"
 
 namespace crvae {
 
@@ -27,9 +26,9 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;    // 16384
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;    // 24576
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 81920
 constexpr int TC_TMEM_COLS = 512;   // two 192-column accumulators (double buffered)
-constexpr int EPI_LD = 33;          // padded row of the per-warp 32x32 epilogue transpose slab (floats)
-constexpr int TC_SLAB_BYTES = 4 * 32 * EPI_LD * 4;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_EPI_WARPS = 8;     // lane quadrant x half of the gate columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct ProjTcArgs {
     float* C;               // gates + t_skip*B*G
@@ -40,15 +39,16 @@ struct ProjTcArgs {
 
 // PERSISTENT: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  The TMA ring runs
 // continuously across tiles and the accumulator is double buffered in TMEM, so the epilogue of tile i (TMEM ->
-// registers -> per-warp smem transpose -> coalesced 128-byte stores) overlaps the MMAs of tile i+1.
-__global__ void __launch_bounds__(192, 1)
+// registers -> 256-bit stores) overlaps the MMAs of tile i+1.  The gate rows of W_ih arrive PERMUTED inside every
+// 32-block (crvae_split_tf32_gate_rows), so the 8 accumulator columns a thread's 16x256b fragment holds are 8
+// consecutive gate columns: each quad stores one full 128-byte line per row, no shared-memory transpose.
+__global__ void __launch_bounds__(TC_THREADS, 1)
 proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, ProjTcArgs a) {
     using namespace umma;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset form keeps the shared address space (LDS/STS, not generic LD/ST)
-    float* slabs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_SLAB_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* empty = full + TC_STAGES;
     uint64_t* tmem_full = empty + TC_STAGES;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -63,7 +63,7 @@ proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -122,33 +122,42 @@ proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         }
     } else {
         const int q = warp & 3;                     // TMEM lane quadrant this warp may access
-        float* slab = slabs + q * (32 * EPI_LD);
+        const int chalf = (warp - 2) >> 2;          // gate columns [96 chalf, 96 chalf + 96)
+        const int tr = lane >> 2, tq = lane & 3;
         int i = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++i) {
             const int head = tile / a.n_mtiles, m_tile = tile % a.n_mtiles;
             const int ab = i & 1;
+            const float* bias = a.bias + static_cast<long long>(head) * TC_BN + 96 * chalf + 8 * tq;
+            float bv[3][8];
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 32 * f)), b1 = __ldg(reinterpret_cast<const float4*>(bias + 32 * f) + 1);
+                bv[f][0] = b0.x; bv[f][1] = b0.y; bv[f][2] = b0.z; bv[f][3] = b0.w; bv[f][4] = b1.x; bv[f][5] = b1.y; bv[f][6] = b1.z; bv[f][7] = b1.w;
+            }
             mbar_wait(&tmem_full[ab], (i >> 1) & 1);
             tc_fence_after();
-            const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * TC_BN);
-            const float* bias = a.bias + static_cast<long long>(head) * TC_BN;
-            const int row_base = m_tile * TC_BM + q * 32;
-            float* cbase = a.C + static_cast<long long>(head) * a.c_head_stride + static_cast<long long>(row_base) * TC_BN;
-            int nrows = a.M - row_base;
-            nrows = nrows < 0 ? 0 : (nrows > 32 ? 32 : nrows);
-#pragma unroll 1
-            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                float v[32];
-                tmem_ld_32x32(acc + static_cast<uint32_t>(c0), v);
-                tmem_ld_wait();
-                // lane = row in TMEM; transpose the 32x32 block through smem so every global store is one 128-byte line
+            const int row_base = m_tile * TC_BM + q * 32 + tr;
+            float* cbase = a.C + static_cast<long long>(head) * a.c_head_stride + 96 * chalf + 8 * tq;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) slab[lane * EPI_LD + j] = v[j];
-                __syncwarp();
-                const float bv = __ldg(bias + c0 + lane);
-#pragma unroll 8
-                for (int rr = 0; rr < nrows; ++rr)
-                    cbase[static_cast<long long>(rr) * TC_BN + c0 + lane] = slab[rr * EPI_LD + lane] + bv;
-                __syncwarp();
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32 + 16 * hh) << 16) + static_cast<uint32_t>(ab * TC_BN + 96 * chalf);
+                float v[3][16];
+#pragma unroll
+                for (int f = 0; f < 3; ++f) tmem_ld_16x32(acc + static_cast<uint32_t>(32 * f), v[f]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = row_base + 16 * hh + 8 * rr;
+                    if (row < a.M) {
+                        float* dst = cbase + static_cast<long long>(row) * TC_BN;
+                        const int k0 = 2 * rr;      // fragment register of unit m: k0 + 4(m >> 1) + (m & 1)
+#pragma unroll
+                        for (int f = 0; f < 3; ++f)
+                            stg_v8(dst + 32 * f, v[f][k0] + bv[f][0], v[f][k0 + 1] + bv[f][1], v[f][k0 + 4] + bv[f][2], v[f][k0 + 5] + bv[f][3],
+                                   v[f][k0 + 8] + bv[f][4], v[f][k0 + 9] + bv[f][5], v[f][k0 + 12] + bv[f][6], v[f][k0 + 13] + bv[f][7]);
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -159,6 +168,21 @@ proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+    }
+}
+
+// same split, rows permuted inside every 32-row block: row r of src lands at row pos_of_unit(r) (gru_tc_common.cuh)
+__global__ void split_tf32_gate_rows_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long rows,
+                                            int cols) {
+    const long long n = rows * cols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / cols;
+        const int c = static_cast<int>(e - r * cols);
+        const long long rd = (r & ~31LL) | pos_of_unit(static_cast<int>(r & 31));
+        const float v = src[e];
+        const float hf = tf32_rna(v);
+        hi[rd * cols + c] = hf;
+        lo[rd * cols + c] = __fsub_rn(v, hf);
     }
 }
 
@@ -246,13 +270,24 @@ extern "C" int crvae_split_tf32(const float* src, float* hi, float* lo, int64_t 
     return check_launch("split_tf32_kernel");
 }
 
+extern "C" int crvae_split_tf32_gate_rows(const float* src, float* hi, float* lo, int64_t rows, int cols, void* stream) {
+    CRVAE_REQUIRE(src && hi && lo && rows >= 0 && cols > 0, "bad argument");
+    CRVAE_REQUIRE(rows % 32 == 0, "rows must be a multiple of 32 (gate rows: 192 per head)");
+    CRVAE_REQUIRE(src != hi && src != lo, "the permuting split cannot run in place");
+    if (rows == 0) return 0;
+    long long blocks = (rows * cols + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    split_tf32_gate_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, hi, lo, rows, cols);
+    return check_launch("split_tf32_gate_rows_kernel");
+}
+
 extern "C" int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
                                  const float* b_ih, float* gates, int P, int T, int B, int K, int t_skip, void* stream) {
     CRVAE_REQUIRE(x_hi && x_lo && w_hi && w_lo && b_ih && gates, "null operand");
     CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0 && K > 0 && t_skip >= 0 && t_skip <= T, "bad size");
     CRVAE_REQUIRE(K % 4 == 0, "tensor-core projection needs K % 4 == 0 (16-byte TMA row pitch); use crvae_proj_fwd");
-    CRVAE_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo) && aligned16(gates) && aligned16(b_ih),
-                  "16-byte alignment");
+    CRVAE_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo) && aligned16(b_ih), "16-byte alignment");
+    CRVAE_REQUIRE((reinterpret_cast<uintptr_t>(gates) & 31u) == 0, "gates must be 32-byte aligned (256-bit stores)");
     const int M = (T - t_skip) * B;
     if (P == 0 || M == 0) return 0;
     const long long xoff = (long long)t_skip * B * K;
@@ -287,6 +322,6 @@ extern "C" int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const flo
     }
     int grid = n_tiles < num_sms ? n_tiles : num_sms;
     if (n_tiles >= 2 * num_sms && grid > reserve + 8) grid -= reserve;
-    proj_fwd_tc_kernel<<<grid, 192, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+    proj_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
     return check_launch("proj_fwd_tc_kernel");
 }

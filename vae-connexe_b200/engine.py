@@ -236,7 +236,7 @@ class CRVAEEngine:
         if self.proj_mode == "tc3":
             x_hi, x_lo = (self.enc_in_hi, self.enc_in_lo) if which == "enc" else (self.dec_in_hi, self.dec_in_lo)
             w_hi, w_lo = (self.enc_w_hi, self.enc_w_lo) if which == "enc" else (self.w_ih_hi, self.w_ih_lo)
-            k.split_tf32(w, w_hi, w_lo, w.numel())          # weights change every iteration
+            k.split_tf32_gate_rows(w, w_hi, w_lo, P * G, self.p)      # weights change every iteration; rows permuted for the epilogue
             k.proj_fwd_tc(x_hi, x_lo, w_hi, w_lo, b, gates, P, T, self.B, self.p, t_skip)
         else:
             k.proj_fwd(x, w, b, gates, P, T, self.B, self.p, t_skip)

@@ -29,6 +29,7 @@ SIGNATURES = {
     "crvae_proj_wgrad_tc_workspace": (_c_size_t, [_c_int] * 5),
     "crvae_proj_wgrad_tc": (_c_int, [_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
     "crvae_split_tf32": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_void_p]),
+    "crvae_split_tf32_gate_rows": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_int, _c_void_p]),
     "crvae_proj_wgrad_workspace": (_c_size_t, [_c_int] * 4),
     "crvae_proj_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
     "crvae_gru_fwd": (_c_int, [_c_void_p] * 5 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
@@ -151,6 +152,9 @@ class Kernels:
     def proj_wgrad_tc(self, dgates, x_hi, x_lo, mask, dw_ih, P, T, B, K, t_skip, ws=None):
         self._ck(self.lib.crvae_proj_wgrad_tc(ptr(dgates), ptr(x_hi), ptr(x_lo), ptr(mask), ptr(dw_ih), P, T, B, K, t_skip,
                                               ptr(ws), stream_ptr()), "crvae_proj_wgrad_tc")
+
+    def split_tf32_gate_rows(self, src, hi, lo, rows, cols):
+        self._ck(self.lib.crvae_split_tf32_gate_rows(ptr(src), ptr(hi), ptr(lo), rows, cols, stream_ptr()), "crvae_split_tf32_gate_rows")
 
     def split_tf32(self, src, hi, lo, n):
         self._ck(self.lib.crvae_split_tf32(ptr(src), ptr(hi), ptr(lo), n, stream_ptr()), "crvae_split_tf32")
