@@ -126,17 +126,19 @@ __global__ void __launch_bounds__(256) gd_prox_gc_kernel(float* __restrict__ w, 
     const int head = blockIdx.y, j = blockIdx.x * 32 + tx;
     const bool live = j < K;
     const bool keep = live && (mask == nullptr || mask[(long long)head * K + j] != 0);
-    float v[24];
+    float v[24], d[24];
     double ss = 0.0;
+    // all 48 loads of the thread go out before the first use (one memory round trip instead of 24)
+    const long long idx0 = ((long long)head * G + ty) * K + (keep ? j : 0);
 #pragma unroll
     for (int q = 0; q < 24; ++q) {
-        const int g = ty + 8 * q;
-        const long long idx = ((long long)head * G + g) * K + j;
-        float x = 0.f;
-        if (keep) {
-            x = w[idx];
-            if (dw) x = __fsub_rn(x, __fmul_rn(lr, dw[idx]));
-        }
+        v[q] = keep ? __ldcs(w + idx0 + (long long)(8 * q) * K) : 0.f;
+        d[q] = (keep && dw) ? __ldcs(dw + idx0 + (long long)(8 * q) * K) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 24; ++q) {
+        float x = v[q];
+        if (dw) x = __fsub_rn(x, __fmul_rn(lr, d[q]));
         v[q] = x;
         ss += (double)x * (double)x;
     }
