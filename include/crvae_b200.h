@@ -193,6 +193,17 @@ int crvae_latent_bwd(const float* dh0, int P, const float* dz_extra, const float
                      const float* eps, float beta, int kl_form, float* dlat, float* dz_out,
                      int B, int Z, void* stream);
 
+/* The same latent head for H = Z = 64 (CR-VAE, VRAE4E) fused with its two Linear layers, one launch each:
+ *   fwd: lat = hT . lat_w^T + lat_b (fc_mu | fc_std, :210-211), z, KL as crvae_latent_fwd
+ *   bwd: d_lat_w = dlat^T . hT, d_lat_b = column sums of dlat, dhT = dlat . lat_w          (autograd, :497)
+ * hT [B,64], lat_w [128,64], lat_b [128], lat/dlat [B,128].  workspace: crvae_latent_head_workspace(B) bytes,
+ * zero-filled once by the caller (per-CTA KL partials + a completion counter the kernel resets itself).      */
+size_t crvae_latent_head_workspace(int B);
+int crvae_latent_head_fwd(const float* hT, const float* lat_w, const float* lat_b, const float* eps, float* lat,
+                          float* z, float* kl_out, int B, int kl_form, void* workspace, void* stream);
+int crvae_latent_head_bwd(const float* dlat, const float* hT, const float* lat_w, float* d_lat_w, float* d_lat_b,
+                          float* dhT, int B, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused MSE loss forward + backward for all heads (trainer :484, :509; nn.MSELoss 'mean'):
  *   sse[i]         = sum_{t,b} (pred[i][t][b] - target[i][t][b])^2     (loss = sum_i sse[i]/(T*B))

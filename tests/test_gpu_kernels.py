@@ -397,3 +397,29 @@ def test_cs_divergence_fwd_bwd(B, K):
     assert float((dl.cpu() - dl_ref).abs().max()) < 1e-4 * scale
     assert float((dm.cpu() - dm_ref).abs().max()) < 1e-4 * float(dm_ref.abs().max())
     assert float((dv.cpu() - dv_ref).abs().max()) < 1e-4 * float(dv_ref.abs().max())
+
+
+@pytest.mark.parametrize("B,kl_form", [(256, 1), (100, 0), (16, 1), (300, 1)])
+def test_latent_head_fused(B, kl_form):
+    """Fused fc_mu|fc_std + reparameterisation + KL (forward) and its three gradient products (backward) against fp64 torch."""
+    k = _k()
+    hT, w, b, eps = _rand(B, H, seed=1), _rand(2 * H, H, seed=2, scale=0.125), _rand(2 * H, seed=3, scale=0.1), _rand(B, H, seed=4)
+    c = lambda t: t.cuda()
+    lat, z, kl = torch.zeros(B, 2 * H, device="cuda"), torch.zeros(B, H, device="cuda"), torch.zeros(1, device="cuda")
+    ws = torch.zeros(k.latent_head_workspace(B) // 4 + 4, device="cuda")
+    for _ in range(2):      # twice: the completion counter must reset itself
+        k.latent_head_fwd(c(hT), c(w), c(b), c(eps), lat, z, kl, B, kl_form, ws)
+    torch.cuda.synchronize()
+    lat_ref = hT.double() @ w.double().T + b.double()
+    mu, lv = lat_ref[:, :H], lat_ref[:, H:]
+    z_ref = mu + torch.exp(0.5 * lv) * eps.double()
+    kl_ref = (-0.5 * (1 + mu - lv * lv - torch.exp(mu))).sum() / B if kl_form == 1 else (-0.5 * (1 + lv - mu * mu - torch.exp(lv))).sum() / B
+    assert _rel(lat, lat_ref) < 2e-6 and _rel(z, z_ref) < 2e-6
+    assert abs(float(kl) - float(kl_ref)) < 2e-6 * abs(float(kl_ref)) + 1e-6
+    dlat = _rand(B, 2 * H, seed=5)
+    dW, db, dhT = torch.zeros(2 * H, H, device="cuda"), torch.zeros(2 * H, device="cuda"), torch.zeros(B, H, device="cuda")
+    k.latent_head_bwd(c(dlat), c(hT), c(w), dW, db, dhT, B)
+    torch.cuda.synchronize()
+    assert _rel(dW, dlat.double().T @ hT.double()) < 2e-6
+    assert _rel(db, dlat.double().sum(0)) < 2e-6
+    assert _rel(dhT, dlat.double() @ w.double()) < 2e-6

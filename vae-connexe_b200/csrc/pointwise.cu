@@ -53,6 +53,13 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dh0, int P, const fl
     if (e >= n) return;
     float dz = 0.f;
     int i = 0;
+    for (; i + 16 <= P; i += 16) {              // 16 loads in flight, added in head order (fixed)
+        float a[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) a[u] = __ldcs(dh0 + (long long)(i + u) * n + e);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) dz += a[u];
+    }
     for (; i + 4 <= P; i += 4) {
         float a0 = dh0[(long long)i * n + e], a1 = dh0[(long long)(i + 1) * n + e];
         float a2 = dh0[(long long)(i + 2) * n + e], a3 = dh0[(long long)(i + 3) * n + e];
@@ -297,7 +304,7 @@ extern "C" int crvae_latent_bwd(const float* dh0, int P, const float* dz_extra, 
     CRVAE_REQUIRE(B > 0 && Z > 0 && P >= 0 && (P == 0 || dh0), "bad argument");
     CRVAE_REQUIRE(dlat == nullptr || (lat && eps), "lat/eps required with dlat");
     int n = B * Z;
-    latent_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dh0, P, dz_extra, lat, eps, beta, kl_form,
+    latent_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dh0, P, dz_extra, lat, eps, beta, kl_form,
                                                                          dlat, dz_out, B, Z);
     return check_launch("latent_bwd_kernel");
 }

@@ -166,6 +166,9 @@ class CRVAEEngine:
                      k.proj_wgrad_workspace(1, ENC_STEPS, B, self.p))
         self.ws_wgrad = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)
         self.ws_wgrad_dec = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)   # side-stream twin
+        self.ws_lat = None
+        if hasattr(k, "latent_head_fwd"):
+            self.ws_lat = torch.zeros(k.latent_head_workspace(B) // 4 + 4, dtype=torch.float32, device=dev)
         self.ws_wgrad_tc = self.ws_dwhh = None
         if hasattr(k, "proj_wgrad_tc_workspace") and P > 0:     # split-reduction partials of the tensor-core gradient GEMMs
             self.ws_wgrad_tc = torch.zeros(k.proj_wgrad_tc_workspace(P, DEC_STEPS, B, self.p, 1) // 4 + 4, dtype=torch.float32, device=dev)
@@ -189,8 +192,11 @@ class CRVAEEngine:
                       self.enc_hs, self.enc_ghn, None, 1, ENC_STEPS, B, 0)
             hT = self.enc_hs[0, ENC_STEPS - 1]
             # [mu | log_var] = h_T [fc_mu ; fc_std]^T + b (:210-211); z = mu + exp(.5 lv) eps (:213-216); KL (:486)
-            k.gemm(L.GEMM_NT, 1, B, 2 * H, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * H, 0, th["lat_b"], 0)
-            k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, self.kl_form)
+            if self.ws_lat is not None:     # fused: one launch instead of GEMM + pointwise on the latency-bound chain
+                k.latent_head_fwd(hT, th["lat_w"], th["lat_b"], self.eps, self.lat, self.zlat, self.kl, B, self.kl_form, self.ws_lat)
+            else:
+                k.gemm(L.GEMM_NT, 1, B, 2 * H, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * H, 0, th["lat_b"], 0)
+                k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, self.kl_form)
         if P > 0:
             self._project(self.dec_in, "dec", th["w_ih"], th["b_ih"], self.gates, P, DEC_STEPS, 1)
         self._join(side)
@@ -290,9 +296,12 @@ class CRVAEEngine:
                 k.axpy(self.dlat, dlat_extra, B * 2 * H, 1.0)
             hT = self.enc_hs[0, ENC_STEPS - 1]
             # fc_mu|fc_std: dW = dlat^T hT, db = column sums, dhT = dlat W
-            k.gemm(L.GEMM_TN, 1, 2 * H, H, B, self.dlat, 2 * H, 0, hT, H, 0, g["lat_w"], H, 0)
-            k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
-            k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
+            if self.ws_lat is not None:
+                k.latent_head_bwd(self.dlat, hT, th["lat_w"], g["lat_w"], g["lat_b"], self.dhT, B)
+            else:
+                k.gemm(L.GEMM_TN, 1, 2 * H, H, B, self.dlat, 2 * H, 0, hT, H, 0, g["lat_w"], H, 0)
+                k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
+                k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
             # encoder BPTT: gradient enters only through h_T
             k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
                       None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,

@@ -41,6 +41,9 @@ SIGNATURES = {
     "crvae_gru_dwhh_tc_workspace": (_c_size_t, [_c_int] * 3),
     "crvae_gru_dwhh_tc": (_c_int, [_c_void_p] * 4 + [_c_i64, _c_void_p] + [_c_int] * 3 + [_c_void_p, _c_void_p]),
     "crvae_latent_fwd": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_int, _c_void_p]),
+    "crvae_latent_head_workspace": (_c_size_t, [_c_int]),
+    "crvae_latent_head_fwd": (_c_int, [_c_void_p] * 7 + [_c_int, _c_int, _c_void_p, _c_void_p]),
+    "crvae_latent_head_bwd": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p]),
     "crvae_latent_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_void_p,
                                   _c_void_p, _c_int, _c_int, _c_void_p]),
     "crvae_mse_fwd_bwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 3 + [_c_float, _c_void_p]),
@@ -206,6 +209,17 @@ class Kernels:
     def latent_fwd(self, lat, eps, z, kl_out, B, kl_form, Z=64):
         self._ck(self.lib.crvae_latent_fwd(ptr(lat), ptr(eps), ptr(z), ptr(kl_out), B, Z, kl_form, stream_ptr()),
                  "crvae_latent_fwd")
+
+    def latent_head_workspace(self, B) -> int:
+        return int(self.lib.crvae_latent_head_workspace(B))
+
+    def latent_head_fwd(self, hT, lat_w, lat_b, eps, lat, z, kl_out, B, kl_form, ws):
+        self._ck(self.lib.crvae_latent_head_fwd(ptr(hT), ptr(lat_w), ptr(lat_b), ptr(eps), ptr(lat), ptr(z), ptr(kl_out), B, kl_form,
+                                                ptr(ws), stream_ptr()), "crvae_latent_head_fwd")
+
+    def latent_head_bwd(self, dlat, hT, lat_w, d_lat_w, d_lat_b, dhT, B):
+        self._ck(self.lib.crvae_latent_head_bwd(ptr(dlat), ptr(hT), ptr(lat_w), ptr(d_lat_w), ptr(d_lat_b), ptr(dhT), B, stream_ptr()),
+                 "crvae_latent_head_bwd")
 
     def latent_bwd(self, dh0, P, dz_extra, lat, eps, beta, kl_form, dlat, dz_out, B, Z=64):
         self._ck(self.lib.crvae_latent_bwd(ptr(dh0), P, ptr(dz_extra), ptr(lat), ptr(eps), float(beta), kl_form,
