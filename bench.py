@@ -173,7 +173,7 @@ def profile_stages(run, eps_list, reps):
     eng, k = run.eng, run.eng.k
     names, evs = [], []
     orig = {}
-    stage_fns = ["proj_fwd", "proj_fwd_tc", "split_tf32", "proj_wgrad_tc", "gru_fwd_tc", "gru_bwd_deferred", "gru_bwd_tc", "gru_dwhh_tc", "gru_fwd", "gemm", "latent_fwd", "mse_fwd_bwd", "dot_small", "gru_bwd", "proj_wgrad", "latent_bwd",
+    stage_fns = ["proj_fwd", "proj_fwd_tc", "split_tf32", "proj_wgrad_tc", "gru_fwd_tc", "gru_bwd_deferred", "gru_bwd_tc", "gru_dwhh_tc", "gru_fwd", "gemm", "latent_fwd", "latent_head_fwd", "latent_head_bwd", "mse_fwd_bwd", "dot_small", "gru_bwd", "proj_wgrad", "latent_bwd",
                  "gd_prox_gc", "gd_step", "axpy"]
     records = []
 
