@@ -274,6 +274,13 @@ void crvae_debug_set_batch_tile(int rows);
 /* grad += 2*lam_ridge*theta (gradient of the ridge term in `smooth`, :488/:513-515)             */
 int crvae_axpy(float* y, const float* x, int64_t n, float alpha, void* stream);
 
+/* Batch binding (the layouts arrange_input's windows are streamed in; :208 encoder input X[:,0:Te], :119 decoder input
+ * [0, X[:,Te:Te+Td-1]], :484 per-head targets X[:,Te:,i]) in one pass:
+ *   X [B,Te+Td,p] -> enc_in [Te,B,p], dec_in [Td,B,p] (step 0 is left untouched = zeros), optional tf32 hi|lo splits of
+ *   both (NULL, NULL to skip), target [P,Td,B] for heads head_lo .. head_lo+P-1.                                        */
+int crvae_bind_batch(const float* X, float* enc_in, float* enc_hi, float* enc_lo, float* dec_in, float* dec_hi,
+                     float* dec_lo, float* target, int B, int p, int Te, int Td, int head_lo, int P, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

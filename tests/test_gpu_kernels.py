@@ -423,3 +423,22 @@ def test_latent_head_fused(B, kl_form):
     assert _rel(dW, dlat.double().T @ hT.double()) < 2e-6
     assert _rel(db, dlat.double().sum(0)) < 2e-6
     assert _rel(dhT, dlat.double() @ w.double()) < 2e-6
+
+
+@pytest.mark.parametrize("B,p,head_lo,P", [(256, 100, 0, 100), (40, 12, 3, 5), (70, 130, 120, 10), (33, 260, 0, 0)])
+def test_bind_batch_fused(B, p, head_lo, P):
+    """One-pass batch binding (time-major inputs + tf32 splits + per-head targets) against the torch reshapes."""
+    k = _k()
+    Te = Td = 10
+    X = _rand(B, Te + Td, p, seed=1).cuda()
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    enc, eh, el, dec, dh, dl = z(Te, B, p), z(Te, B, p), z(Te, B, p), z(Td, B, p), z(Td, B, p), z(Td, B, p)
+    tgt = z(max(P, 1), Td, B)
+    k.bind_batch(X, enc, eh, el, dec, dh, dl, tgt, B, p, Te, Td, head_lo, P)
+    torch.cuda.synchronize()
+    assert torch.equal(enc, X[:, :Te].transpose(0, 1))
+    assert torch.equal(dec[1:], X[:, Te:-1].transpose(0, 1)) and float(dec[0].abs().sum()) == 0
+    assert torch.equal(eh + el, enc) and torch.equal(dh + dl, dec)
+    assert float((eh.view(torch.int32) & 0x1FFF).abs().sum()) == 0 and float((dh.view(torch.int32) & 0x1FFF).abs().sum()) == 0
+    if P > 0:
+        assert torch.equal(tgt[:P], X[:, Te:, head_lo:head_lo + P].permute(2, 1, 0))

@@ -215,6 +215,37 @@ def test_cuda_graph_replay_equals_eager(traj):
     assert torch.equal(finals[0][0], finals[1][0]) and finals[0][1] == finals[1][1]     # deterministic kernels
 
 
+def test_host_fed_iteration_equals_device_fed(traj):
+    """Phase1Runner.iterate_from_host (pinned host batch + noise through the double-buffered copy stream, loss back into a
+    pinned ring) gives bit-identical weights and losses to the device-fed iterate()."""
+    import vae_connexe_b200 as V
+    p, B = 10, 256
+    wins = O.arrange_input(torch.from_numpy(traj["data"].T.copy()), 20)[0]
+    Xh = wins[traj["idx"]].contiguous().pin_memory()
+    gen = torch.Generator().manual_seed(3)
+    eps_h = torch.randn(8, B, H, generator=gen).pin_memory()
+    finals = []
+    for host_fed in (False, True):
+        torch.manual_seed(0)
+        m = V.CRVAE(p, np.ones((p, p)), 64)
+        run = V.Phase1Runner(m, Xh.cuda(), 5e-2, 0.1, 0.0, 0.1, use_graphs=True)
+        run.forward(eps_h[0].cuda())
+        run.update(); run.forward(eps_h[1].cuda()); run.capture()
+        losses = []
+        for k in range(2, 8):
+            if host_fed:
+                slot = run.iterate_from_host(Xh, eps_h[k])
+            else:
+                run.iterate(eps_h[k].cuda())
+                losses.append(float(m.engine.loss))
+        if host_fed:
+            ring = run.losses_from_host()
+            losses = [float(ring[i]) for i in range(6)]
+            assert slot == 5
+        finals.append((m.engine.theta.flat.clone(), losses))
+    assert torch.equal(finals[0][0], finals[1][0]) and finals[0][1] == finals[1][1]
+
+
 def test_p4_train_phase1_tracks_golden_log(traj):
     """P4 (first 301 iterations of the golden 5000-iteration run, incl. the 100% -> 52% usage
     collapse): our train_phase1 with the reference's seeds reproduces the reference's check-block

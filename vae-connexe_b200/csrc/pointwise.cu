@@ -287,6 +287,60 @@ static inline int grid_for(long long n, int block = 256, int cap = 148 * 8) {
     return (int)b;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Batch binding: the window batch X [B, Te+Td, p] -> time-major encoder / decoder inputs (+ their tf32 hi | lo
+// splits for the tensor-core projection) and the per-head targets, in one pass (arrange of :208 / :119 / :484).
+// Block = (32 batch rows, one step, 128 columns) staged through shared memory so every global access is coalesced.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bind_batch_kernel(const float* __restrict__ X, float* __restrict__ enc_in,
+                                                         float* __restrict__ enc_hi, float* __restrict__ enc_lo,
+                                                         float* __restrict__ dec_in, float* __restrict__ dec_hi,
+                                                         float* __restrict__ dec_lo, float* __restrict__ target, int B, int p,
+                                                         int Te, int Td, int head_lo, int P) {
+    __shared__ float tile[32][129];
+    const int b0 = blockIdx.x * 32, t = blockIdx.y, c0 = blockIdx.z * 128;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int b = b0 + r;
+        for (int c = tx; c < 128; c += 32)
+            tile[r][c] = (b < B && c0 + c < p) ? __ldg(X + ((long long)b * (Te + Td) + t) * p + c0 + c) : 0.f;
+    }
+    __syncthreads();
+    float *dst = nullptr, *dhi = nullptr, *dlo = nullptr;
+    if (t < Te) {
+        dst = enc_in + (long long)t * B * p; dhi = enc_hi ? enc_hi + (long long)t * B * p : nullptr; dlo = enc_lo ? enc_lo + (long long)t * B * p : nullptr;
+    } else if (t < Te + Td - 1) {        // decoder step s = t - Te + 1 sees x_{t}; step 0 stays zero
+        const long long off = (long long)(t - Te + 1) * B * p;
+        dst = dec_in + off; dhi = dec_hi ? dec_hi + off : nullptr; dlo = dec_lo ? dec_lo + off : nullptr;
+    }
+    if (dst) {
+        for (int r = ty; r < 32; r += 8) {
+            const int b = b0 + r;
+            if (b >= B) continue;
+            for (int c = tx; c < 128 && c0 + c < p; c += 32) {
+                const float v = tile[r][c];
+                const long long o = (long long)b * p + c0 + c;
+                dst[o] = v;
+                if (dhi) {
+                    uint32_t h;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+                    const float hf = __uint_as_float(h);
+                    dhi[o] = hf;
+                    dlo[o] = __fsub_rn(v, hf);
+                }
+            }
+        }
+    }
+    if (t >= Te && target) {             // target[i][t - Te][b] = X[b][t][head_lo + i]
+        for (int c = ty; c < 128; c += 8) {
+            const int i = c0 + c - head_lo;
+            if (i < 0 || i >= P || b0 + tx >= B) continue;
+            target[((long long)i * Td + (t - Te)) * B + b0 + tx] = tile[tx][c];
+        }
+    }
+}
+
 }  // namespace crvae
 
 using namespace crvae;
@@ -413,4 +467,15 @@ extern "C" int crvae_act_bwd(const float* dy, const float* y, float* dx, int64_t
     if (n == 0) return 0;
     act_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n, kind);
     return check_launch("act_bwd_kernel");
+}
+
+extern "C" int crvae_bind_batch(const float* X, float* enc_in, float* enc_hi, float* enc_lo, float* dec_in, float* dec_hi,
+                                float* dec_lo, float* target, int B, int p, int Te, int Td, int head_lo, int P, void* stream) {
+    CRVAE_REQUIRE(X && enc_in && dec_in && B > 0 && p > 0 && Te > 0 && Td > 0 && P >= 0 && head_lo >= 0, "bad argument");
+    CRVAE_REQUIRE((enc_hi == nullptr) == (enc_lo == nullptr) && (dec_hi == nullptr) == (dec_lo == nullptr), "hi/lo go together");
+    CRVAE_REQUIRE(P == 0 || target, "target missing");
+    dim3 grid((B + 31) / 32, Te + Td, (p + 127) / 128);
+    bind_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, enc_in, enc_hi, enc_lo, dec_in, dec_hi, dec_lo, P > 0 ? target : nullptr, B, p,
+                                                              Te, Td, head_lo, P);
+    return check_launch("bind_batch_kernel");
 }

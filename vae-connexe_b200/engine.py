@@ -118,14 +118,20 @@ class CRVAEEngine:
             self.dec_in = torch.zeros(DEC_STEPS, B, self.p, dtype=torch.float32, device=self.device)
             self.target = torch.empty(max(self.P, 1), DEC_STEPS, B, dtype=torch.float32, device=self.device)
         # in-place (re)binding keeps the buffer addresses stable for captured CUDA graphs
+        tc = self.proj_mode == "tc3"
+        if tc and (getattr(self, "enc_in_hi", None) is None or self.enc_in_hi.shape != self.enc_in.shape):
+            self.enc_in_hi, self.enc_in_lo = torch.zeros_like(self.enc_in), torch.zeros_like(self.enc_in)
+            self.dec_in_hi, self.dec_in_lo = torch.zeros_like(self.dec_in), torch.zeros_like(self.dec_in)
+        if hasattr(self.k, "bind_batch") and X.is_contiguous():      # one pass: transposes + tf32 splits + targets
+            self.k.bind_batch(X, self.enc_in, self.enc_in_hi if tc else None, self.enc_in_lo if tc else None, self.dec_in,
+                              self.dec_in_hi if tc else None, self.dec_in_lo if tc else None, self.target, B, self.p,
+                              ENC_STEPS, DEC_STEPS, lo, self.P)
+            return
         self.enc_in.copy_(X[:, :ENC_STEPS].transpose(0, 1))                               # [Te,B,p]
         self.dec_in[1:].copy_(X[:, ENC_STEPS:-1].transpose(0, 1))                         # [Td,B,p], step 0 stays 0
         if self.P > 0:
             self.target[: self.P].copy_(X[:, ENC_STEPS:, lo:hi].permute(2, 1, 0))         # [P,Td,B]
-        if self.proj_mode == "tc3":      # the batch is fixed (:470-473): split it into tf32 hi/lo once
-            if getattr(self, "enc_in_hi", None) is None or self.enc_in_hi.shape != self.enc_in.shape:
-                self.enc_in_hi, self.enc_in_lo = torch.empty_like(self.enc_in), torch.empty_like(self.enc_in)
-                self.dec_in_hi, self.dec_in_lo = torch.empty_like(self.dec_in), torch.empty_like(self.dec_in)
+        if tc:      # the batch is fixed (:470-473): split it into tf32 hi/lo once
             self.k.split_tf32(self.enc_in, self.enc_in_hi, self.enc_in_lo, self.enc_in.numel())
             self.k.split_tf32(self.dec_in, self.dec_in_hi, self.dec_in_lo, self.dec_in.numel())
 

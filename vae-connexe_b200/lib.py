@@ -28,6 +28,7 @@ SIGNATURES = {
     "crvae_proj_fwd_tc": (_c_int, [_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p]),
     "crvae_proj_wgrad_tc_workspace": (_c_size_t, [_c_int] * 5),
     "crvae_proj_wgrad_tc": (_c_int, [_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p, _c_void_p]),
+    "crvae_bind_batch": (_c_int, [_c_void_p] * 8 + [_c_int] * 6 + [_c_void_p]),
     "crvae_split_tf32": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_void_p]),
     "crvae_split_tf32_gate_rows": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_int, _c_void_p]),
     "crvae_proj_wgrad_workspace": (_c_size_t, [_c_int] * 4),
@@ -155,6 +156,10 @@ class Kernels:
     def proj_wgrad_tc(self, dgates, x_hi, x_lo, mask, dw_ih, P, T, B, K, t_skip, ws=None):
         self._ck(self.lib.crvae_proj_wgrad_tc(ptr(dgates), ptr(x_hi), ptr(x_lo), ptr(mask), ptr(dw_ih), P, T, B, K, t_skip,
                                               ptr(ws), stream_ptr()), "crvae_proj_wgrad_tc")
+
+    def bind_batch(self, X, enc_in, enc_hi, enc_lo, dec_in, dec_hi, dec_lo, target, B, p, Te, Td, head_lo, P):
+        self._ck(self.lib.crvae_bind_batch(ptr(X), ptr(enc_in), ptr(enc_hi), ptr(enc_lo), ptr(dec_in), ptr(dec_hi), ptr(dec_lo),
+                                           ptr(target), B, p, Te, Td, head_lo, P, stream_ptr()), "crvae_bind_batch")
 
     def split_tf32_gate_rows(self, src, hi, lo, rows, cols):
         self._ck(self.lib.crvae_split_tf32_gate_rows(ptr(src), ptr(hi), ptr(lo), rows, cols, stream_ptr()), "crvae_split_tf32_gate_rows")

@@ -102,6 +102,44 @@ class Phase1Runner:
             self.update()
             self.forward_noeps()
 
+    # ------------------------------------------------------------------ host-fed pipeline
+    def iterate_from_host(self, X_host: torch.Tensor, eps_host: torch.Tensor) -> int:
+        """One iteration whose window batch (B, 20, p) and noise (B, H) come from PINNED HOST memory and whose loss goes
+        back to the host, without stalling the device: the two H2D copies run on a copy stream into one of two staging
+        slots (so the copy of iteration i+1 overlaps the kernels of iteration i), the compute stream waits on the copy
+        event, re-binds the batch and replays the iteration, and the loss is copied (async) into a pinned ring.  Returns
+        the ring index of this iteration's loss; `losses_from_host()` synchronises and returns the ring."""
+        dev = self.eng.device
+        st = getattr(self, "_host", None)
+        if st is None or st["X"][0].shape != X_host.shape:
+            st = self._host = {
+                "copy": torch.cuda.Stream(device=dev),
+                "X": [torch.empty(X_host.shape, dtype=torch.float32, device=dev) for _ in range(2)],
+                "eps": [torch.empty(eps_host.shape, dtype=torch.float32, device=dev) for _ in range(2)],
+                "copied": [torch.cuda.Event() for _ in range(2)], "consumed": [torch.cuda.Event() for _ in range(2)],
+                "loss": torch.zeros(4096, dtype=torch.float32).pin_memory(), "i": 0}
+            for ev in st["consumed"]:
+                ev.record(torch.cuda.current_stream(dev))
+        i = st["i"]; j = i & 1
+        with torch.cuda.stream(st["copy"]):
+            st["copy"].wait_event(st["consumed"][j])                  # slot j was last read two iterations ago
+            st["X"][j].copy_(X_host, non_blocking=True)
+            st["eps"][j].copy_(eps_host, non_blocking=True)
+            st["copied"][j].record(st["copy"])
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(st["copied"][j])
+        self.eng.bind_batch(st["X"][j])
+        self.iterate(st["eps"][j])
+        st["consumed"][j].record(cur)
+        slot = i % st["loss"].numel()
+        st["loss"][slot:slot + 1].copy_(self.eng.loss, non_blocking=True)
+        st["i"] = i + 1
+        return slot
+
+    def losses_from_host(self) -> torch.Tensor:
+        torch.cuda.synchronize(self.eng.device)
+        return self._host["loss"]
+
     def run_update(self):
         if self.g_update is not None:
             self.g_update.replay()
