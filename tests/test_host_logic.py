@@ -337,3 +337,25 @@ def test_generic_vrae_tracks_reference(cpu_backend):
         model(data, teacher_forcing_ratio=0.5)
     s = model.sample(4, 7)
     assert s.shape == (4, 7, 10)
+
+
+def test_driver_phase_handoff_wire_format(cpu_backend, traj, tmp_path):
+    """The reference driver (:730-796) as vae_connexe_b200.driver.run: the series file and GC_lorenz96.npy keep the
+    reference's on-disk formats, phase 2 can start from a graph file written by the reference (here: the golden GC)."""
+    from vae_connexe_b200 import driver
+    p = 10
+    np.save(tmp_path / driver.DATA_FILE, traj["data"])                       # (p, T) float32, as the reference saves it (:744)
+    torch.manual_seed(0); np.random.seed(0)
+    out = driver.run(workdir=str(tmp_path), p=p, max_iter_phase1=51, check_every=50, phases=(1,), device="cpu", verbose=0)
+    gc = np.load(tmp_path / driver.GC_FILE)
+    assert gc.dtype == np.int32 and gc.shape == (p, p) and np.array_equal(gc, out["GC_est"])
+    assert np.array_equal(out["GC_true"], driver.lorenz_96_graph(p)) and out["GC_true"].sum() == 4 * p
+    # a graph written by the reference: int32 (p, p); heads read its COLUMNS (:201)
+    ref_gc = traj["final_GC"].astype(np.int32)                               # the golden 5000-iteration graph (sha d11a29d6...)
+    assert ref_gc.shape == (p, p) and 0 < ref_gc.sum() < p * p
+    np.save(tmp_path / driver.GC_FILE, ref_gc)
+    torch.manual_seed(0); np.random.seed(0)
+    out2 = driver.run(workdir=str(tmp_path), p=p, max_iter_phase2=3, check_every=50, phases=(2,), device="cpu", verbose=0)
+    assert np.array_equal(out2["GC_est"], ref_gc) and out2["loss_phase2"] is not None
+    with pytest.raises(ValueError):
+        driver.load_gc(str(tmp_path / driver.GC_FILE), p=7)
