@@ -52,8 +52,8 @@ gru_fwd_tc_kernel(GruTcArgs a, const float* __restrict__ w_hi, const float* __re
     float* pred_s = reinterpret_cast<float*>(smem + GT_OFF_PRED);
     float* bih_s = reinterpret_cast<float*>(smem + GT_OFF_CONST);
     float* bhh_s = bih_s + GG;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);      // accumulator complete (tcgen05.commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + GT_OFF_BAR);      // [3] gate r | z | n accumulator complete (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -68,7 +68,7 @@ gru_fwd_tc_kernel(GruTcArgs a, const float* __restrict__ w_hi, const float* __re
                                 : (has_lin ? __ldg(a.w_lin + (long long)head * GH + (e - 2 * GG)) : 0.f);
     if (warp == 0) {
         if (lane == 0) {
-            mbar_init(mbar, 1);
+            for (int g = 0; g < 3; ++g) mbar_init(&mbar[g], 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -116,26 +116,30 @@ gru_fwd_tc_kernel(GruTcArgs a, const float* __restrict__ w_hi, const float* __re
     float h[16], gi[3][16];
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * q + 16 * hh) << 16) + static_cast<uint32_t>(32 * cg);
 
-    auto load_gi = [&](int t) {
+    // gi of gate g for step t -> gi[g] (bias only while t < t_skip)
+    auto load_gi_gate = [&](int t, int g) {
         if (t < a.t_skip) {
 #pragma unroll
-            for (int g = 0; g < 3; ++g)
-#pragma unroll
-                for (int k = 0; k < 16; ++k) gi[g][k] = bih_s[g * GH + ucol + 2 * (k >> 2) + (k & 1)];
+            for (int k = 0; k < 16; ++k) gi[g][k] = bih_s[g * GH + ucol + 2 * (k >> 2) + (k & 1)];
             return;
         }
-        const float* gbase = a.gates + ((long long)head * a.T + t) * a.B * GG + ucol;
+        const float* gbase = a.gates + ((long long)head * a.T + t) * a.B * GG + g * GH + ucol;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int b = brow0 + 8 * rr;
-            const float* grow = gbase + (long long)b * GG;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (b < a.B) ldg_v8_stream(gbase + (long long)b * GG, v);
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (b < a.B) ldg_v8_stream(grow + g * GH, v);
+            for (int m = 0; m < 8; ++m) gi[g][4 * (m >> 1) + 2 * rr + (m & 1)] = v[m];
+        }
+    };
+    // a 16-register fragment (2 rows x 8 units) -> rows brow0, brow0 + 8 of a row-major buffer (256-bit stores)
+    auto store_frag = [&](float* base, int ld, const float* f) {
 #pragma unroll
-                for (int m = 0; m < 8; ++m) gi[g][4 * (m >> 1) + 2 * rr + (m & 1)] = v[m];
-            }
+        for (int rr = 0; rr < 2; ++rr) {
+            const int b = brow0 + 8 * rr;
+            const int k0 = 2 * rr;          // register of unit m: k0 + 4(m >> 1) + (m & 1)
+            if (b < a.B) stg_v8(base + (long long)b * ld, f[k0], f[k0 + 1], f[k0 + 4], f[k0 + 5], f[k0 + 8], f[k0 + 9], f[k0 + 12], f[k0 + 13]);
         }
     };
     auto store_h_operand = [&]() {     // h (registers) -> TMEM A operand, tf32 hi | lo
@@ -149,20 +153,25 @@ gru_fwd_tc_kernel(GruTcArgs a, const float* __restrict__ w_hi, const float* __re
         tmem_st_16x32(lane_addr + GT_ACOL_LO, lo);
         tmem_st_wait();
     };
-    auto issue_step = [&]() {          // thread 0: the 24 MMAs of one step
+    // thread 0: the gate GEMM of one step, gate by gate (3 x 8 K-steps x 3 MMAs of N = 64) with one commit per gate, so
+    // the pointwise warps start on r while the tensor core is still working on z and n
+    auto issue_step = [&]() {
         tc_fence_after();
-        constexpr uint32_t idesc = idesc_tf32(GT_ROWS, GG, false, false);
+        constexpr uint32_t idesc = idesc_tf32(GT_ROWS, GH, false, false);
         const uint32_t w_hi_s = smem_u32(smem + GT_OFF_WHI), w_lo_s = smem_u32(smem + GT_OFF_WLO);
-        const uint32_t acc = tmem_base + GT_DCOL;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t offB = (kk >> 2) * GT_W_HALF + (kk & 3) * 32;
-            const uint32_t a_hi = tmem_base + GT_ACOL_HI + kk * 8, a_lo = tmem_base + GT_ACOL_LO + kk * 8;
-            mma_tf32_ts(acc, a_lo, smem_desc_k_sw128(w_hi_s + offB), idesc, kk != 0);
-            mma_tf32_ts(acc, a_hi, smem_desc_k_sw128(w_lo_s + offB), idesc, true);
-            mma_tf32_ts(acc, a_hi, smem_desc_k_sw128(w_hi_s + offB), idesc, true);
+        for (int g = 0; g < 3; ++g) {
+            const uint32_t acc = tmem_base + GT_DCOL + g * GH;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint32_t offB = (kk >> 2) * GT_W_HALF + g * GH * 128 + (kk & 3) * 32;
+                const uint32_t a_hi = tmem_base + GT_ACOL_HI + kk * 8, a_lo = tmem_base + GT_ACOL_LO + kk * 8;
+                mma_tf32_ts(acc, a_lo, smem_desc_k_sw128(w_hi_s + offB), idesc, kk != 0);
+                mma_tf32_ts(acc, a_hi, smem_desc_k_sw128(w_lo_s + offB), idesc, true);
+                mma_tf32_ts(acc, a_hi, smem_desc_k_sw128(w_hi_s + offB), idesc, true);
+            }
+            mma_commit(&mbar[g]);
         }
-        mma_commit(mbar);
     };
 
     // h0 -> registers -> operand
@@ -182,67 +191,74 @@ gru_fwd_tc_kernel(GruTcArgs a, const float* __restrict__ w_hi, const float* __re
         }
     }
     store_h_operand();
-    load_gi(0);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) load_gi_gate(0, g);
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) issue_step();
 
     for (int t = 0; t < a.T; ++t) {
         const long long trow = ((long long)head * a.T + t) * a.B;       // global row of (head, t, b = 0)
-        mbar_wait(mbar, t & 1);
-        tc_fence_after();
         float* pred_t = pred_s + (t & 1) * GT_ROWS * 2;
         {
-            float ar[16], az[16];
+            // The LSU queue is in order: a prefetch issued after the step's stores waits for all of them to drain.  So every
+            // gate's result is stored, and the same gate's gi of step t+1 requested, as soon as that gate is done.
+            float ar[16], az[16], an[16];
+            const bool more = t + 1 < a.T;
+            mbar_wait(&mbar[0], t & 1);
+            tc_fence_after();
             tmem_ld_16x32(lane_addr + GT_DCOL, ar);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int m = 2 * (k >> 2) + (k & 1);      // unit offset of register k
+                ar[k] = sigmoidf_fast(gi[0][k] + (ar[k] + bhh_s[ucol + m]));          // r
+            }
+            store_frag(a.gates + trow * GG + ucol, GG, ar);
+            if (more) load_gi_gate(t + 1, 0);
+            mbar_wait(&mbar[1], t & 1);
+            tc_fence_after();
             tmem_ld_16x32(lane_addr + GT_DCOL + GH, az);
             tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {                 // r, z replace gi_r, gi_z
-                const int m = 2 * (k >> 2) + (k & 1);      // unit offset of register k
-                gi[0][k] = sigmoidf_fast(gi[0][k] + (ar[k] + bhh_s[ucol + m]));
-                gi[1][k] = sigmoidf_fast(gi[1][k] + (az[k] + bhh_s[GH + ucol + m]));
+            for (int k = 0; k < 16; ++k) {
+                const int m = 2 * (k >> 2) + (k & 1);
+                az[k] = sigmoidf_fast(gi[1][k] + (az[k] + bhh_s[GH + ucol + m]));     // z
             }
-            tmem_ld_16x32(lane_addr + GT_DCOL + 2 * GH, ar);
+            store_frag(a.gates + trow * GG + GH + ucol, GG, az);
+            if (more) load_gi_gate(t + 1, 1);
+            mbar_wait(&mbar[2], t & 1);
+            tc_fence_after();
+            tmem_ld_16x32(lane_addr + GT_DCOL + 2 * GH, an);
             tmem_ld_wait();
             float ps[2] = {0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {                 // gh_n replaces the accumulator, n replaces gi_n
                 const int m = 2 * (k >> 2) + (k & 1);
-                const float ghn_ = ar[k] + bhh_s[2 * GH + ucol + m];
-                const float n = tanhf_fast(__fadd_rn(gi[2][k], __fmul_rn(gi[0][k], ghn_)));
-                const float hn = __fadd_rn(__fmul_rn(__fsub_rn(h[k], n), gi[1][k]), n);
+                const float ghn_ = an[k] + bhh_s[2 * GH + ucol + m];
+                const float n = tanhf_fast(__fadd_rn(gi[2][k], __fmul_rn(ar[k], ghn_)));
+                const float hn = __fadd_rn(__fmul_rn(__fsub_rn(h[k], n), az[k]), n);
                 h[k] = hn;
-                ar[k] = ghn_;
+                an[k] = ghn_;
                 gi[2][k] = n;
                 ps[(k >> 1) & 1] = fmaf(hn, wl[m], ps[(k >> 1) & 1]);
             }
+            store_frag(a.gates + trow * GG + 2 * GH + ucol, GG, gi[2]);
+            if (more) {
+                load_gi_gate(t + 1, 2);
+                store_h_operand();
+            }
+            store_frag(a.ghn + trow * GH + ucol, GH, an);
+            store_frag(a.hs + trow * GH + ucol, GH, h);
+            if (has_lin) {
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int b = brow0 + 8 * rr;
-                if (b < a.B) {
-                    const long long grow = trow + b;
-                    float* gdst = a.gates + grow * GG + ucol;
-                    const int k0 = 2 * rr;      // register of unit m: k0 + 4(m >> 1) + (m & 1)
-#pragma unroll
-                    for (int g = 0; g < 3; ++g)
-                        stg_v8(gdst + g * GH, gi[g][k0], gi[g][k0 + 1], gi[g][k0 + 4], gi[g][k0 + 5], gi[g][k0 + 8], gi[g][k0 + 9],
-                               gi[g][k0 + 12], gi[g][k0 + 13]);
-                    stg_v8(a.ghn + grow * GH + ucol, ar[k0], ar[k0 + 1], ar[k0 + 4], ar[k0 + 5], ar[k0 + 8], ar[k0 + 9], ar[k0 + 12],
-                           ar[k0 + 13]);
-                    stg_v8(a.hs + grow * GH + ucol, h[k0], h[k0 + 1], h[k0 + 4], h[k0 + 5], h[k0 + 8], h[k0 + 9], h[k0 + 12], h[k0 + 13]);
-                }
-                if (has_lin) {
+                for (int rr = 0; rr < 2; ++rr) {
                     float p = ps[rr];
                     p += __shfl_xor_sync(0xffffffffu, p, 1);
                     p += __shfl_xor_sync(0xffffffffu, p, 2);
                     if (tq == 0) pred_t[(32 * q + 16 * hh + tr + 8 * rr) * 2 + cg] = p;
                 }
             }
-        }
-        if (t + 1 < a.T) {
-            store_h_operand();
-            load_gi(t + 1);            // in flight across the barrier and the next gate GEMM
         }
         tc_fence_before();             // accumulator reads / operand writes of this step are complete
         __syncthreads();
