@@ -245,11 +245,23 @@ class Phase2Runner:
         self.g_full = self.g_update = self.g_fwd = None
 
     def update(self):
-        self.v.backward(self.beta_e)                  # smooth_e.backward() (:611)
-        if self.lam == 0:
-            self.v.adam_step()                        # optimizer.step(); optimizer.zero_grad() (:612-614)
+        # The two backward passes are independent (:611-623 touch disjoint parameters): the VRAE4E chain (some thirty small,
+        # latency-bound launches) runs on a twin stream next to the CRVAE's big kernels; fork / join are capturable.
+        twin = None
+        if self.c.device.type == "cuda" and self.c.use_side_stream:
+            if getattr(self, "_twin", None) is None:
+                self._twin = torch.cuda.Stream(device=self.c.device)
+            twin = self._twin
+            ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream()); twin.wait_event(ev)
+        import contextlib
+        with (torch.cuda.stream(twin) if twin is not None else contextlib.nullcontext()):
+            self.v.backward(self.beta_e)                  # smooth_e.backward() (:611)
+            if self.lam == 0:
+                self.v.adam_step()                        # optimizer.step(); optimizer.zero_grad() (:612-614)
         self.c.backward(self.beta, self.lam_ridge)    # smooth.backward() (:616)
         self.c.step(self.lr, self.lam)                # GD (:617-618) + prox (:621-623)
+        if twin is not None:
+            ev = torch.cuda.Event(); ev.record(twin); torch.cuda.current_stream().wait_event(ev)
 
     def forward_staged(self):
         self.c.forward_staged(want_err=True)          # :630-637

@@ -58,6 +58,7 @@ class VRAE4EEngine:
         self.sse, self.kl, self.loss = z(1), z(1), z(1)
         self.ones_B, self.ones_TB = torch.ones(B, 1, device=dev), torch.ones(STEPS * B, 1, device=dev)
         k = self.k
+        self.ws_lat = torch.zeros(k.latent_head_workspace(B) // 4 + 4, dtype=torch.float32, device=dev) if hasattr(k, "latent_head_fwd") else None
         self.ws_gru = torch.zeros(k.gru_bwd_workspace(1, B) // 4 + 4, dtype=torch.float32, device=dev)
         self.ws_wgrad = torch.zeros(k.proj_wgrad_workspace(1, STEPS, B, p_) // 4 + 4, dtype=torch.float32, device=dev)
 
@@ -78,8 +79,11 @@ class VRAE4EEngine:
         k.gru_fwd(self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
                   self.enc_hs, self.enc_ghn, None, 1, STEPS, B, 0)
         hT = self.enc_hs[0, STEPS - 1]
-        k.gemm(L.GEMM_NT, 1, B, 2 * H, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * H, 0, th["lat_b"], 0)      # :157-158
-        k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, self.kl_form)                                   # :160-163
+        if self.ws_lat is not None:      # fused fc_mu|fc_std + reparameterisation + KL (:157-163), one launch
+            k.latent_head_fwd(hT, th["lat_w"], th["lat_b"], self.eps, self.lat, self.zlat, self.kl, B, self.kl_form, self.ws_lat)
+        else:
+            k.gemm(L.GEMM_NT, 1, B, 2 * H, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * H, 0, th["lat_b"], 0)      # :157-158
+            k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, self.kl_form)                                   # :160-163
         k.gemm(L.GEMM_NT, 1, B, H, H, self.zlat, H, 0, th["hid_w"], H, 0, self.pre, H, 0, th["hid_b"], 0)       # :164
         k.tanh_fwd(self.pre, self.zh, B * H)
         k.proj_fwd(self.dec_in, th["dec_w_ih"], th["dec_b_ih"], self.dec_gates, 1, STEPS, B, p_, 1)
@@ -110,9 +114,12 @@ class VRAE4EEngine:
         if dlat_extra is not None:
             k.axpy(self.dlat, dlat_extra, B * 2 * H, 1.0)
         hT = self.enc_hs[0, STEPS - 1]
-        k.gemm(L.GEMM_TN, 1, 2 * H, H, B, self.dlat, 2 * H, 0, hT, H, 0, g["lat_w"], H, 0)
-        k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
-        k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
+        if self.ws_lat is not None:
+            k.latent_head_bwd(self.dlat, hT, th["lat_w"], g["lat_w"], g["lat_b"], self.dhT, B)
+        else:
+            k.gemm(L.GEMM_TN, 1, 2 * H, H, B, self.dlat, 2 * H, 0, hT, H, 0, g["lat_w"], H, 0)
+            k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
+            k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
         k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT, None,
                   g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0, 1, STEPS, B, self.ws_gru)
         k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, STEPS, B, p_, 0, self.ws_wgrad)
