@@ -73,6 +73,27 @@ __global__ void __launch_bounds__(256, 2) gru_fwd_kernel(GruFwdArgs a) {
         // Blackwell issues fp32 FMAs at full rate only as packed pairs (FFMA2, fma.rn.f32x2): accumulators are float2
         // over adjacent gate columns, the hidden value is broadcast into both halves.  Per-component results are
         // bit-identical to scalar fmaf.
+        float gi[RB][12];
+        auto load_gi = [&]() {
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                int gb = b_tile + ty * RB + i;
+                if (t < a.t_skip || gb >= a.B) {
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) gi[i][q] = bih[q];
+                } else {
+                    const float* src = a.gates + (row0 + gb) * G + j0;
+#pragma unroll
+                    for (int gt = 0; gt < 3; ++gt) {
+                        float4 v = *reinterpret_cast<const float4*>(src + gt * H);
+                        gi[i][gt * 4 + 0] = v.x; gi[i][gt * 4 + 1] = v.y; gi[i][gt * 4 + 2] = v.z; gi[i][gt * 4 + 3] = v.w;
+                    }
+                }
+            }
+        };
+        // 16-row tiles (RB == 1) are the latency-bound shapes (encoder, P = 1): gi is requested BEFORE the matmul so the
+        // global round trip hides behind it.  Larger tiles fetch it after (see below).
+        if (RB == 1) load_gi();
         float2 acc2[RB][6];
 #pragma unroll
         for (int i = 0; i < RB; ++i)
@@ -99,24 +120,9 @@ __global__ void __launch_bounds__(256, 2) gru_fwd_kernel(GruFwdArgs a) {
         for (int i = 0; i < RB; ++i)
 #pragma unroll
             for (int q = 0; q < 6; ++q) { acc[i][2 * q] = acc2[i][q].x; acc[i][2 * q + 1] = acc2[i][q].y; }
-        // gi is fetched AFTER the matmul: its latency is covered by the second CTA resident on the SM, and not
+        // RB > 1: gi is fetched AFTER the matmul: its latency is covered by the second CTA resident on the SM, and not
         // holding 12*RB registers across the K loop is what lets two CTAs fit (<= 128 registers per thread)
-        float gi[RB][12];
-#pragma unroll
-        for (int i = 0; i < RB; ++i) {
-            int gb = b_tile + ty * RB + i;
-            if (t < a.t_skip || gb >= a.B) {
-#pragma unroll
-                for (int q = 0; q < 12; ++q) gi[i][q] = bih[q];
-            } else {
-                const float* src = a.gates + (row0 + gb) * G + j0;
-#pragma unroll
-                for (int gt = 0; gt < 3; ++gt) {
-                    float4 v = *reinterpret_cast<const float4*>(src + gt * H);
-                    gi[i][gt * 4 + 0] = v.x; gi[i][gt * 4 + 1] = v.y; gi[i][gt * 4 + 2] = v.z; gi[i][gt * 4 + 3] = v.w;
-                }
-            }
-        }
+        if (RB != 1) load_gi();
         // gate math; operation order h' = (h - n)*z + n reproduces ATen's CPU GRU
         float hnew[RB][4], rr[RB][4], zz[RB][4], nn[RB][4], gn[RB][4];
 #pragma unroll
@@ -242,6 +248,10 @@ __global__ void __launch_bounds__(256, DEFER_DW ? 2 : 1) gru_bwd_kernel(GruBwdAr
     }
     __syncthreads();
 
+    float4 pf[6];                    // RB == 1 only: r | z | n | gh_n | h_{t-2} | dhs of step t-1, requested one step ahead
+    float pf_dp = 0.f, pf_dpm1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) pf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = a.T - 1; t >= 0; --t) {
         const long long row0 = ((long long)head * a.T + t) * a.B;
         const long long rowP = ((long long)head * a.T + (t - 1)) * a.B;   // rows of h_{t-1} when t > 0
@@ -252,6 +262,9 @@ __global__ void __launch_bounds__(256, DEFER_DW ? 2 : 1) gru_bwd_kernel(GruBwdAr
             const int lb = ty * RB + i, gb = b_tile + lb;
             float4 r4, z4, n4, gn4, hp4, de4 = make_float4(0.f, 0.f, 0.f, 0.f);
             float dp = 0.f, dpm1 = 0.f;
+            if (RB == 1 && t != a.T - 1) {      // 16-row tiles: the inputs were requested during the previous step's matmuls
+                r4 = pf[0]; z4 = pf[1]; n4 = pf[2]; gn4 = pf[3]; hp4 = pf[4]; de4 = pf[5]; dp = pf_dp; dpm1 = pf_dpm1;
+            } else
             if (gb < a.B) {
                 const float* gsrc = a.gates + (row0 + gb) * G + j0;
                 r4 = *reinterpret_cast<const float4*>(gsrc);
@@ -305,6 +318,28 @@ __global__ void __launch_bounds__(256, DEFER_DW ? 2 : 1) gru_bwd_kernel(GruBwdAr
             }
         }
         __syncthreads();
+        if (RB == 1 && t > 0) {          // inputs of step t-1: in flight across both matmuls of this step
+            const int gb = b_tile + ty;
+            const int tp = t - 1;
+            const long long r0p = ((long long)head * a.T + tp) * a.B, rPp = ((long long)head * a.T + (tp - 1)) * a.B;
+            pf_dp = 0.f; pf_dpm1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) pf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gb < a.B) {
+                const float* gsrc = a.gates + (r0p + gb) * G + j0;
+                pf[0] = *reinterpret_cast<const float4*>(gsrc);
+                pf[1] = *reinterpret_cast<const float4*>(gsrc + H);
+                pf[2] = *reinterpret_cast<const float4*>(gsrc + 2 * H);
+                pf[3] = *reinterpret_cast<const float4*>(a.ghn + (r0p + gb) * H + j0);
+                pf[4] = tp > 0 ? *reinterpret_cast<const float4*>(a.hs + (rPp + gb) * H + j0)
+                               : *reinterpret_cast<const float4*>(h0 + (long long)gb * H + j0);
+                if (has_lin) {
+                    pf_dp = __ldg(a.dpred + r0p + gb);
+                    if (tp > 0) pf_dpm1 = __ldg(a.dpred + rPp + gb);
+                }
+                if (a.dhs) pf[5] = *reinterpret_cast<const float4*>(a.dhs + (r0p + gb) * H + j0);
+            }
+        }
         // ---- matmul 1: dh_{t-1}[b][k] = dh_t*z + sum_g dgh[b][g] * W_hh[g][k] ----
         float2 dh2[RB][2];
 #pragma unroll
