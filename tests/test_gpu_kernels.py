@@ -69,7 +69,9 @@ def test_projection_fwd_and_wgrad(P, T, B, K, t_skip):
 
 
 @pytest.mark.parametrize("P,T,B,K,t_skip", [(1, 10, 256, 100, 0), (3, 10, 64, 12, 1), (5, 10, 256, 100, 1), (2, 4, 40, 36, 1),
-                                            (100, 10, 256, 100, 1), (2, 10, 256, 1000, 1)])
+                                            (100, 10, 256, 100, 1), (2, 10, 256, 1000, 1),
+                                            # resident-W variant (K = 32 nfull + tail <= 8, many row tiles per head, grid full)
+                                            (30, 10, 256, 68, 1), (40, 10, 200, 64, 0), (30, 10, 256, 40, 1), (33, 10, 300, 100, 1)])
 def test_projection_tensor_core_3xtf32(P, T, B, K, t_skip):
     """tcgen05 + TMA projection (3xTF32) against the fp64 result: fp32-grade accuracy required."""
     k = _k()

@@ -128,6 +128,17 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                           // layout type SWIZZLE_128B
     return d;
 }
+// K-major tile with 32-byte rows (8 tf32 = one MMA K-step), SWIZZLE_32B (TMA CU_TENSOR_MAP_SWIZZLE_32B), 8-row groups
+// 256 B apart: the narrow tail chunk of a reduction whose depth is not a multiple of 32.
+__device__ __forceinline__ uint64_t smem_desc_k_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(256 >> 4) << 32;                    // stride byte offset: 8 rows x 32 B
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(6) << 61;                           // layout type SWIZZLE_32B
+    return d;
+}
 // MN-major tf32 tile.  For 32-bit MN-major operands the only swizzled layout the tensor core accepts is
 // SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of
 // 128 B hold 32 consecutive M/N elements of ONE k index, 32-byte granules XOR-ed with (row mod 4); 4 k-rows

@@ -37,6 +37,55 @@ struct ProjTcArgs {
     int M, K, n_mtiles, n_tiles;
 };
 
+// Epilogue warps (shared by both projection kernels): accumulator `ab` of tile number i -> + bias -> 256-bit stores.
+// Tiles are first, first + step, ... (< last).
+__device__ __forceinline__ void proj_epilogue(const ProjTcArgs& a, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp,
+                                              int lane, int first, int step, int last) {
+    using namespace umma;
+        const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+        const int chalf = (warp - 2) >> 2;          // gate columns [96 chalf, 96 chalf + 96)
+        const int tr = lane >> 2, tq = lane & 3;
+        int i = 0;
+        for (int tile = first; tile < last; tile += step, ++i) {
+            const int head = tile / a.n_mtiles, m_tile = tile % a.n_mtiles;
+            const int ab = i & 1;
+            const float* bias = a.bias + static_cast<long long>(head) * TC_BN + 96 * chalf + 8 * tq;
+            float bv[3][8];
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 32 * f)), b1 = __ldg(reinterpret_cast<const float4*>(bias + 32 * f) + 1);
+                bv[f][0] = b0.x; bv[f][1] = b0.y; bv[f][2] = b0.z; bv[f][3] = b0.w; bv[f][4] = b1.x; bv[f][5] = b1.y; bv[f][6] = b1.z; bv[f][7] = b1.w;
+            }
+            mbar_wait(&tmem_full[ab], (i >> 1) & 1);
+            tc_fence_after();
+            const int row_base = m_tile * TC_BM + q * 32 + tr;
+            float* cbase = a.C + static_cast<long long>(head) * a.c_head_stride + 96 * chalf + 8 * tq;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32 + 16 * hh) << 16) + static_cast<uint32_t>(ab * TC_BN + 96 * chalf);
+                float v[3][16];
+#pragma unroll
+                for (int f = 0; f < 3; ++f) tmem_ld_16x32(acc + static_cast<uint32_t>(32 * f), v[f]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = row_base + 16 * hh + 8 * rr;
+                    if (row < a.M) {
+                        float* dst = cbase + static_cast<long long>(row) * TC_BN;
+                        const int k0 = 2 * rr;      // fragment register of unit m: k0 + 4(m >> 1) + (m & 1)
+#pragma unroll
+                        for (int f = 0; f < 3; ++f)
+                            stg_v8(dst + 32 * f, v[f][k0] + bv[f][0], v[f][k0 + 1] + bv[f][1], v[f][k0 + 4] + bv[f][2], v[f][k0 + 5] + bv[f][3],
+                                   v[f][k0 + 8] + bv[f][4], v[f][k0 + 9] + bv[f][5], v[f][k0 + 12] + bv[f][6], v[f][k0 + 13] + bv[f][7]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+        }
+}
+
 // PERSISTENT: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  The TMA ring runs
 // continuously across tiles and the accumulator is double buffered in TMEM, so the epilogue of tile i (TMEM ->
 // registers -> 256-bit stores) overlaps the MMAs of tile i+1.  The gate rows of W_ih arrive PERMUTED inside every
@@ -121,48 +170,155 @@ proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             }
         }
     } else {
-        const int q = warp & 3;                     // TMEM lane quadrant this warp may access
-        const int chalf = (warp - 2) >> 2;          // gate columns [96 chalf, 96 chalf + 96)
-        const int tr = lane >> 2, tq = lane & 3;
-        int i = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++i) {
-            const int head = tile / a.n_mtiles, m_tile = tile % a.n_mtiles;
-            const int ab = i & 1;
-            const float* bias = a.bias + static_cast<long long>(head) * TC_BN + 96 * chalf + 8 * tq;
-            float bv[3][8];
-#pragma unroll
-            for (int f = 0; f < 3; ++f) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 32 * f)), b1 = __ldg(reinterpret_cast<const float4*>(bias + 32 * f) + 1);
-                bv[f][0] = b0.x; bv[f][1] = b0.y; bv[f][2] = b0.z; bv[f][3] = b0.w; bv[f][4] = b1.x; bv[f][5] = b1.y; bv[f][6] = b1.z; bv[f][7] = b1.w;
-            }
-            mbar_wait(&tmem_full[ab], (i >> 1) & 1);
-            tc_fence_after();
-            const int row_base = m_tile * TC_BM + q * 32 + tr;
-            float* cbase = a.C + static_cast<long long>(head) * a.c_head_stride + 96 * chalf + 8 * tq;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32 + 16 * hh) << 16) + static_cast<uint32_t>(ab * TC_BN + 96 * chalf);
-                float v[3][16];
-#pragma unroll
-                for (int f = 0; f < 3; ++f) tmem_ld_16x32(acc + static_cast<uint32_t>(32 * f), v[f]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int row = row_base + 16 * hh + 8 * rr;
-                    if (row < a.M) {
-                        float* dst = cbase + static_cast<long long>(row) * TC_BN;
-                        const int k0 = 2 * rr;      // fragment register of unit m: k0 + 4(m >> 1) + (m & 1)
-#pragma unroll
-                        for (int f = 0; f < 3; ++f)
-                            stg_v8(dst + 32 * f, v[f][k0] + bv[f][0], v[f][k0 + 1] + bv[f][1], v[f][k0 + 4] + bv[f][2], v[f][k0 + 5] + bv[f][3],
-                                   v[f][k0 + 8] + bv[f][4], v[f][k0 + 9] + bv[f][5], v[f][k0 + 12] + bv[f][6], v[f][k0 + 13] + bv[f][7]);
+        proj_epilogue(a, tmem_base, tmem_full, tmem_empty, warp, lane, blockIdx.x, gridDim.x, a.n_tiles);
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// RESIDENT-W variant for shallow reductions (K = 32 nfull + tail, nfull <= 3, tail <= 8; K = 100 is 3 x 32 + 4).
+// The streaming kernel above re-fetches W_ih hi | lo (154 KB at K = 100) for each of a head's row tiles -- 256 KB
+// into the SM per 96 KB out, and it is bound by exactly that ingress.  Here every CTA walks a CONTIGUOUS range of
+// tiles (= consecutive row tiles of one head, at most two heads per CTA), keeps the head's W_ih in shared memory
+// (full chunks K-major SWIZZLE_128B; the tail as one 8-wide K-step, SWIZZLE_32B) and streams only x: 102 KB per tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_WCHUNK = 2 * TC_B_BYTES;                 // 49152: W hi | lo of one 32-wide chunk
+constexpr int RS_WTAIL = TC_BN * 32;                      // 6144: [192 rows x 8 k]
+constexpr int RS_OFF_WTAIL = 3 * RS_WCHUNK;               // 147456
+constexpr int RS_OFF_X = RS_OFF_WTAIL + 2 * RS_WTAIL;     // 159744 (1024-aligned)
+constexpr int RS_XSLOT = 2 * TC_A_BYTES;                  // 32768: x hi | lo of one chunk (tail: 4096 + 4096 used)
+constexpr int RS_XTAIL = TC_BM * 32;                      // 4096
+constexpr int RS_SLOTS = 2;
+constexpr int RS_SMEM_BYTES = RS_OFF_X + RS_SLOTS * RS_XSLOT + 1024 + 256;
+
+struct ProjResMaps {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;          // 32-wide boxes, SWIZZLE_128B
+    CUtensorMap at_hi, at_lo, bt_hi, bt_lo;      // 8-wide boxes, SWIZZLE_32B (tail)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+proj_fwd_tc_res_kernel(const __grid_constant__ ProjResMaps tm, ProjTcArgs a, int nfull, int tail) {
+    using namespace umma;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + RS_OFF_X + RS_SLOTS * RS_XSLOT);
+    uint64_t* empty = full + RS_SLOTS;
+    uint64_t* tmem_full = empty + RS_SLOTS;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]
+    uint64_t* w_full = tmem_empty + 2;            // W of the current head landed
+    uint64_t* w_empty = w_full + 1;               // every MMA that reads the current W has completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nch = nfull + (tail > 0 ? 1 : 0);
+    const int t_begin = static_cast<int>((static_cast<long long>(blockIdx.x) * a.n_tiles) / gridDim.x);
+    const int t_end = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * a.n_tiles) / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm.a_hi); prefetch_tmap(&tm.a_lo); prefetch_tmap(&tm.b_hi); prefetch_tmap(&tm.b_lo);
+        prefetch_tmap(&tm.at_hi); prefetch_tmap(&tm.at_lo); prefetch_tmap(&tm.bt_hi); prefetch_tmap(&tm.bt_lo);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < RS_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
+            mbar_init(w_full, 1); mbar_init(w_empty, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<TC_TMEM_COLS>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int c = 0, cur_head = -1, nsw = 0;
+            for (int tile = t_begin; tile < t_end; ++tile) {
+                const int head = tile / a.n_mtiles, m_tile = tile % a.n_mtiles;
+                if (head != cur_head) {
+                    if (nsw > 0) mbar_wait(w_empty, (nsw - 1) & 1);          // the previous head's MMAs are done with W
+                    mbar_arrive_expect_tx(w_full, nfull * RS_WCHUNK + (tail > 0 ? 2 * RS_WTAIL : 0));
+                    for (int kc = 0; kc < nfull; ++kc) {
+                        tma_load_2d(smem + kc * RS_WCHUNK, &tm.b_hi, w_full, kc * 32, head * TC_BN);
+                        tma_load_2d(smem + kc * RS_WCHUNK + TC_B_BYTES, &tm.b_lo, w_full, kc * 32, head * TC_BN);
+                    }
+                    if (tail > 0) {
+                        tma_load_2d(smem + RS_OFF_WTAIL, &tm.bt_hi, w_full, nfull * 32, head * TC_BN);
+                        tma_load_2d(smem + RS_OFF_WTAIL + RS_WTAIL, &tm.bt_lo, w_full, nfull * 32, head * TC_BN);
+                    }
+                    cur_head = head; ++nsw;
+                }
+                for (int kc = 0; kc < nch; ++kc, ++c) {
+                    const int s = c % RS_SLOTS, ph = (c / RS_SLOTS) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + RS_OFF_X + s * RS_XSLOT;
+                    if (kc < nfull) {
+                        mbar_arrive_expect_tx(&full[s], RS_XSLOT);
+                        tma_load_2d(st, &tm.a_hi, &full[s], kc * 32, m_tile * TC_BM);
+                        tma_load_2d(st + TC_A_BYTES, &tm.a_lo, &full[s], kc * 32, m_tile * TC_BM);
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], 2 * RS_XTAIL);
+                        tma_load_2d(st, &tm.at_hi, &full[s], nfull * 32, m_tile * TC_BM);
+                        tma_load_2d(st + RS_XTAIL, &tm.at_lo, &full[s], nfull * 32, m_tile * TC_BM);
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[ab]);
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(TC_BM, TC_BN, false, false);
+            int c = 0, i = 0, cur_head = -1, nsw = 0;
+            for (int tile = t_begin; tile < t_end; ++tile, ++i) {
+                const int head = tile / a.n_mtiles;
+                if (head != cur_head) {
+                    mbar_wait(w_full, nsw & 1);
+                    cur_head = head; ++nsw;
+                }
+                const int ab = i & 1;
+                mbar_wait(&tmem_empty[ab], ((i >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t acc = tmem_base + static_cast<uint32_t>(ab * TC_BN);
+                for (int kc = 0; kc < nch; ++kc, ++c) {
+                    const int s = c % RS_SLOTS, ph = (c / RS_SLOTS) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t xs = smem_u32(smem + RS_OFF_X + s * RS_XSLOT);
+                    if (kc < nfull) {
+                        const uint32_t ws = smem_u32(smem + kc * RS_WCHUNK);
+                        const uint64_t a_hi = smem_desc_k_sw128(xs), a_lo = smem_desc_k_sw128(xs + TC_A_BYTES);
+                        const uint64_t b_hi = smem_desc_k_sw128(ws), b_lo = smem_desc_k_sw128(ws + TC_B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = static_cast<uint64_t>(2 * k);        // 8 tf32 = 32 B = 2 x 16 B
+                            mma_tf32_ss(acc, a_lo + adv, b_hi + adv, idesc, (kc | k) != 0);
+                            mma_tf32_ss(acc, a_hi + adv, b_lo + adv, idesc, true);
+                            mma_tf32_ss(acc, a_hi + adv, b_hi + adv, idesc, true);
+                        }
+                    } else {        // the tail: one K = 8 step on SWIZZLE_32B tiles (columns beyond K are zero-filled by TMA)
+                        const uint32_t ws = smem_u32(smem + RS_OFF_WTAIL);
+                        const uint64_t a_hi = smem_desc_k_sw32(xs), a_lo = smem_desc_k_sw32(xs + RS_XTAIL);
+                        const uint64_t b_hi = smem_desc_k_sw32(ws), b_lo = smem_desc_k_sw32(ws + RS_WTAIL);
+                        mma_tf32_ss(acc, a_lo, b_hi, idesc, kc != 0);
+                        mma_tf32_ss(acc, a_hi, b_lo, idesc, true);
+                        mma_tf32_ss(acc, a_hi, b_hi, idesc, true);
+                    }
+                    mma_commit(&empty[s]);          // smem slot is free once these MMAs have read it
+                }
+                mma_commit(&tmem_full[ab]);         // accumulator complete
+                const bool last_of_head = (tile + 1 == t_end) || ((tile + 1) / a.n_mtiles != head);
+                if (last_of_head) mma_commit(w_empty);
+            }
+        }
+    } else {
+        proj_epilogue(a, tmem_base, tmem_full, tmem_empty, warp, lane, t_begin, 1, t_end);
     }
     __syncthreads();
     if (warp == 1) {
@@ -233,6 +389,23 @@ int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t inner, uint64_t row
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu stride=%llu", (int)r, (unsigned long long)inner,
                   (unsigned long long)rows, (unsigned long long)row_stride_elems);
+        return CRVAE_E_BADARG;
+    }
+    return 0;
+}
+
+// 2D map, 32-byte swizzle (box_inner = 8 floats): the narrow tail chunk of the resident-W projection
+int make_tmap_2d_sw32(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return CRVAE_E_BADARG;
+    cuuint64_t gdim[2] = {inner, rows};
+    cuuint64_t gstr[1] = {row_stride_elems * sizeof(float)};
+    cuuint32_t box[2] = {8, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (32B swizzle) failed (%d)", (int)r);
         return CRVAE_E_BADARG;
     }
     return 0;
@@ -322,6 +495,33 @@ extern "C" int crvae_proj_fwd_tc(const float* x_hi, const float* x_lo, const flo
     }
     int grid = n_tiles < num_sms ? n_tiles : num_sms;
     if (n_tiles >= 2 * num_sms && grid > reserve + 8) grid -= reserve;
+    // shallow reduction + several row tiles per head: keep W_ih resident, stream x only
+    static int res_mode = -1;
+    if (res_mode < 0) {
+        const char* e = getenv("CRVAE_PROJ_RESIDENT");
+        res_mode = e ? atoi(e) : 1;
+    }
+    const int nfull = K / 32, tail = K % 32;
+    if (res_mode && nfull >= 1 && nfull <= 3 && tail <= 8 && n_mtiles >= 4 && n_tiles >= 2 * grid) {
+        ProjResMaps tm;
+        tm.a_hi = tA_hi; tm.a_lo = tA_lo; tm.b_hi = tB_hi; tm.b_lo = tB_lo;
+        if (tail > 0) {
+            if ((rc = make_tmap_2d_sw32(&tm.at_hi, x_hi + xoff, K, M, K, TC_BM))) return rc;
+            if ((rc = make_tmap_2d_sw32(&tm.at_lo, x_lo + xoff, K, M, K, TC_BM))) return rc;
+            if ((rc = make_tmap_2d_sw32(&tm.bt_hi, w_hi, K, (uint64_t)P * TC_BN, K, TC_BN))) return rc;
+            if ((rc = make_tmap_2d_sw32(&tm.bt_lo, w_lo, K, (uint64_t)P * TC_BN, K, TC_BN))) return rc;
+        } else {
+            tm.at_hi = tA_hi; tm.at_lo = tA_lo; tm.bt_hi = tB_hi; tm.bt_lo = tB_lo;
+        }
+        static bool attr2_done = false;
+        if (!attr2_done) {
+            cudaError_t e = cudaFuncSetAttribute(proj_fwd_tc_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES);
+            if (e != cudaSuccess) { set_error("proj_fwd_tc_res smem attr (%d B): %s", RS_SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
+            attr2_done = true;
+        }
+        proj_fwd_tc_res_kernel<<<grid, TC_THREADS, RS_SMEM_BYTES, (cudaStream_t)stream>>>(tm, a, nfull, tail);
+        return check_launch("proj_fwd_tc_res_kernel");
+    }
     proj_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
     return check_launch("proj_fwd_tc_kernel");
 }
