@@ -33,6 +33,8 @@ constexpr int DH_OFF_B = 6 * DH_BLOCK;             // 2 blocks: k 0..63
 constexpr int DH_HALF = 8 * DH_BLOCK;              // 32768 B of raw/hi data, followed by 32768 B of lo data
 constexpr int DH_STAGE_BYTES = 2 * DH_HALF;
 constexpr int DH_TMEM_COLS = 128;
+constexpr int DH_CONV_WARPS = 8;
+constexpr int DH_THREADS = 64 + 32 * DH_CONV_WARPS;
 constexpr int DH_SMEM_BYTES = DH_STAGES * DH_STAGE_BYTES + 1024 + 256;
 
 struct DwhhArgs {
@@ -42,7 +44,7 @@ struct DwhhArgs {
     int splits;        // the T*B rows of a head are cut into `splits` contiguous parts (blockIdx.y)
 };
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(DH_THREADS, 1)
 gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmN,
                    const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmZ, DwhhArgs a) {
     using namespace umma;
@@ -65,7 +67,7 @@ gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmG); prefetch_tmap(&tmN); prefetch_tmap(&tmH); prefetch_tmap(&tmZ); }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < DH_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < DH_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], DH_CONV_WARPS); mbar_init(&empty[s], 1); }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
         }
@@ -119,28 +121,34 @@ gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
             mma_commit(tmem_full);
         }
     } else {
+        // converter warps 0..7 (the conversion chain LDS -> cvt -> STS -> proxy fence -> barrier paces the pipeline: eight
+        // warps, all loads of a thread issued before the first conversion)
         const int cw = warp - 2;
+        constexpr int PER = DH_HALF / 16 / (32 * DH_CONV_WARPS);      // float4 per thread per chunk
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % DH_STAGES, ph = (c / DH_STAGES) & 1;
             mbar_wait(&full[s], ph);
             float4* hi = reinterpret_cast<float4*>(smem + s * DH_STAGE_BYTES);
             float4* lo = reinterpret_cast<float4*>(smem + s * DH_STAGE_BYTES + DH_HALF);
-#pragma unroll 4
-            for (int e = cw * 32 + lane; e < DH_HALF / 16; e += 128) {
-                float4 v = hi[e];
+            float4 v[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) v[i] = hi[cw * 32 + lane + i * 32 * DH_CONV_WARPS];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
                 float4 h, l;
                 uint32_t t;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = __fsub_rn(v.x, h.x);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = __fsub_rn(v.y, h.y);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = __fsub_rn(v.z, h.z);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = __fsub_rn(v.w, h.w);
-                hi[e] = h;
-                lo[e] = l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[i].x)); h.x = __uint_as_float(t); l.x = __fsub_rn(v[i].x, h.x);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[i].y)); h.y = __uint_as_float(t); l.y = __fsub_rn(v[i].y, h.y);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[i].z)); h.z = __uint_as_float(t); l.z = __fsub_rn(v[i].z, h.z);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[i].w)); h.w = __uint_as_float(t); l.w = __fsub_rn(v[i].w, h.w);
+                hi[cw * 32 + lane + i * 32 * DH_CONV_WARPS] = h;
+                lo[cw * 32 + lane + i * 32 * DH_CONV_WARPS] = l;
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&conv[s]);
         }
+        if (warp < 6) {                              // the epilogue needs one warp per TMEM lane quadrant
         // epilogue: accumulator `tile` holds dW_hh rows g = tile*128 + lane-index, 64 columns k
         const int q = warp & 3;
         const int gl = q * 32 + lane;
@@ -166,6 +174,7 @@ gru_dwhh_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
             }
         }
         tc_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -223,7 +232,7 @@ extern "C" int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const f
     const int S = tc_splits_for(P, 1, ((int)TB + DH_BK - 1) / DH_BK, 2);
     if (S > 1) CRVAE_REQUIRE(workspace && aligned16(workspace), "workspace required (crvae_gru_dwhh_tc_workspace)");
     DwhhArgs a{S > 1 ? (float*)workspace : dw_hh, (int)TB, B, h0_head_stride != 0, S};
-    gru_dwhh_tc_kernel<<<dim3(P, S), 192, DH_SMEM_BYTES, (cudaStream_t)stream>>>(tG, tN, tH, tZ, a);
+    gru_dwhh_tc_kernel<<<dim3(P, S), DH_THREADS, DH_SMEM_BYTES, (cudaStream_t)stream>>>(tG, tN, tH, tZ, a);
     rc = check_launch("gru_dwhh_tc_kernel");
     if (rc || S == 1) return rc;
     return launch_split_sum((const float*)workspace, dw_hh, P, S, (long long)DH_G * DH_H, (cudaStream_t)stream);

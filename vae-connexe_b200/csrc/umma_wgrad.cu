@@ -29,13 +29,15 @@ int make_tmap_generic(CUtensorMap* m, const float* base, int rank, const uint64_
 constexpr int WG_BM = 128;                 // input columns k per tile (UMMA M, TMEM lanes)
 constexpr int WG_BN = CRVAE_G;             // 192 gate rows (UMMA N, TMEM columns)
 constexpr int WG_BK = 16;                  // reduction rows (m) per stage (more, smaller stages: deeper TMA pipeline)
-constexpr int WG_STAGES = 4;                // (2 stages + two CTAs per SM measured slower: 111 vs 93 us)
+constexpr int WG_STAGES = 5;                // the pipeline is (stage count x TMA->convert->MMA->release latency) bound: 4 -> 5 stages = 88 -> 80 us
 constexpr int WG_A_BYTES = WG_BM * WG_BK * 4;          // 4 MN-blocks x [WG_BK rows x 128 B]
 constexpr int WG_B_BYTES = WG_BN * WG_BK * 4;          // 6 MN-blocks x [WG_BK rows x 128 B]
 constexpr int WG_BLOCK_BYTES = WG_BK * 128;            // 4096: one MN-block (32 M/N elements) of a stage = LBO
 constexpr int WG_STAGE_BYTES = 2 * WG_A_BYTES + 2 * WG_B_BYTES;
 constexpr int WG_TX_BYTES = 2 * WG_A_BYTES + WG_B_BYTES;   // bytes landed by TMA per stage (B_lo is produced in smem)
 constexpr int WG_TMEM_COLS = 256;
+constexpr int WG_CONV_WARPS = 8;
+constexpr int WG_THREADS = 64 + 32 * WG_CONV_WARPS;
 constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 
 struct WgradTcArgs {
@@ -45,7 +47,7 @@ struct WgradTcArgs {
     int splits;              // the reduction range of a head is cut into `splits` contiguous parts (blockIdx.z)
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                      const __grid_constant__ CUtensorMap tmG, WgradTcArgs a) {
     using namespace umma;
@@ -68,7 +70,7 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmX_hi); prefetch_tmap(&tmX_lo); prefetch_tmap(&tmG); }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], WG_CONV_WARPS); mbar_init(&empty[s], 1); }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
         }
@@ -120,28 +122,35 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
             mma_commit(tmem_full);               // (also fires when this split had no chunks)
         }
     } else {
-        const int cw = warp - 2;                     // converter warp 0..3
+        // converter warps 0..7: dG tile -> tf32 hi (in place) | lo.  The conversion is a latency chain (LDS -> cvt -> STS ->
+        // proxy fence -> barrier) and was the pacing stage of the pipeline with four warps: eight warps, and every thread
+        // issues all of its loads before the first conversion.
+        const int cw = warp - 2;
+        constexpr int PER = WG_B_BYTES / 16 / (32 * WG_CONV_WARPS);      // float4 per thread per chunk
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % WG_STAGES, ph = (c / WG_STAGES) & 1;
             mbar_wait(&full[s], ph);
             float4* hi = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + 2 * WG_A_BYTES);
             float4* lo = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + 2 * WG_A_BYTES + WG_B_BYTES);
-#pragma unroll 4
-            for (int e = cw * 32 + lane; e < WG_B_BYTES / 16; e += 128) {
-                float4 v = hi[e];
+            float4 v[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) v[i] = hi[cw * 32 + lane + i * 32 * WG_CONV_WARPS];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
                 float4 h, l;
                 uint32_t t;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = __fsub_rn(v.x, h.x);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = __fsub_rn(v.y, h.y);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = __fsub_rn(v.z, h.z);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = __fsub_rn(v.w, h.w);
-                hi[e] = h;
-                lo[e] = l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[i].x)); h.x = __uint_as_float(t); l.x = __fsub_rn(v[i].x, h.x);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[i].y)); h.y = __uint_as_float(t); l.y = __fsub_rn(v[i].y, h.y);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[i].z)); h.z = __uint_as_float(t); l.z = __fsub_rn(v[i].z, h.z);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[i].w)); h.w = __uint_as_float(t); l.w = __fsub_rn(v[i].w, h.w);
+                hi[cw * 32 + lane + i * 32 * WG_CONV_WARPS] = h;
+                lo[cw * 32 + lane + i * 32 * WG_CONV_WARPS] = l;
             }
             fence_proxy_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&conv[s]);
         }
+        if (warp < 6) {                              // the epilogue needs one warp per TMEM lane quadrant
         // epilogue: D[lane = k][col = g] -> dW[head][g][k]   (coalesced over lanes for every g)
         const int q = warp & 3;
         const int kcol = k_tile * WG_BM + q * 32 + lane;
@@ -161,6 +170,7 @@ proj_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
             }
         }
         tc_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -235,7 +245,7 @@ extern "C" int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const
     if (S > 1) CRVAE_REQUIRE(workspace && aligned16(workspace), "workspace required (crvae_proj_wgrad_tc_workspace)");
     WgradTcArgs a{S > 1 ? (float*)workspace : dw_ih, mask, K, R, t_skip * B, S};
     dim3 grid((K + WG_BM - 1) / WG_BM, P, S);
-    proj_wgrad_tc_kernel<<<grid, 192, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tX_hi, tX_lo, tG, a);
+    proj_wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tX_hi, tX_lo, tG, a);
     rc = check_launch("proj_wgrad_tc_kernel");
     if (rc || S == 1) return rc;
     return launch_split_sum((const float*)workspace, dw_ih, P, S, (long long)CRVAE_G * K, (cudaStream_t)stream);
