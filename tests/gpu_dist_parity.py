@@ -54,6 +54,34 @@ def main():
             rel = float((vs.engine.theta.flat - v1.engine.theta.flat).abs().max() / v1.engine.theta.flat.abs().max())
             if rel > 1e-4:
                 ok = False; print(f"[rank {rank}] VRAE weights mismatch {rel:.2e}")
+    # phase 1 again at a size where every shard runs the tcgen05 recurrent / projection kernels (>= 8 heads per rank up to
+    # world 8): p = 64 synthetic Lorenz-96, 41 iterations, sharded vs unsharded
+    from vae_connexe_b200.data import lorenz_96
+    p_tc = 64
+    Xtc = torch.tensor(lorenz_96(d=p_tc, t=600, t_eval=0, f=10.0, seed=1).T.copy())[None].cuda()
+    res = []
+    for sharded in (True, False):
+        torch.manual_seed(0); np.random.seed(0)
+        kw = dict(rank=rank, world_size=world, group=dist.group.WORLD) if sharded else {}
+        m = V.CRVAE(p_tc, np.ones((p_tc, p_tc)), 64, **kw)
+        log = []
+        V.train_phase1(m, Xtc, context=20, lam=0.1, lam_ridge=0.0, lr=5e-2, max_iter=41, check_every=20, verbose=0, log=log)
+        res.append((m, log))
+    (ms, logs), (m1, log1) = res
+    if ms.engine.rec_mode != "tc3" and world <= 8:
+        ok = False; print(f"[rank {rank}] expected the tensor-core recurrent path on the shard, got {ms.engine.rec_mode}")
+    for a, b in zip(logs, log1):
+        for key in a:
+            if a[key] is not None and abs(a[key] - b[key]) > 1e-4 * abs(b[key]) + 1e-6:
+                ok = False; print(f"[rank {rank}] tc-size log mismatch", key, a, b)
+    if not torch.equal(ms.GC(), m1.GC()):
+        ok = False; print(f"[rank {rank}] tc-size GC mismatch")
+    sd1 = m1.state_dict()
+    for k, t in ms.state_dict().items():
+        diff = float((t - sd1[k]).abs().max())
+        rel = diff / float(sd1[k].abs().max().clamp_min(1e-30))
+        if rel > 1e-4 and diff > 5e-6:        # (1,)-shaped biases near zero: judge those by the absolute difference
+            ok = False; print(f"[rank {rank}] tc-size weight mismatch {k}: rel {rel:.2e} abs {diff:.2e}")
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
