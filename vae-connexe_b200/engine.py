@@ -175,7 +175,9 @@ class CRVAEEngine:
         self.ws_lat = None
         if hasattr(k, "latent_head_fwd"):
             self.ws_lat = torch.zeros(k.latent_head_workspace(B) // 4 + 4, dtype=torch.float32, device=dev)
-        self.ws_wgrad_tc = self.ws_dwhh = None
+        self.ws_wgrad_tc = self.ws_dwhh = self.ws_wgrad_tc_enc = None
+        if hasattr(k, "proj_wgrad_tc_workspace"):
+            self.ws_wgrad_tc_enc = torch.zeros(k.proj_wgrad_tc_workspace(1, ENC_STEPS, B, self.p, 0) // 4 + 4, dtype=torch.float32, device=dev)
         if hasattr(k, "proj_wgrad_tc_workspace") and P > 0:     # split-reduction partials of the tensor-core gradient GEMMs
             self.ws_wgrad_tc = torch.zeros(k.proj_wgrad_tc_workspace(P, DEC_STEPS, B, self.p, 1) // 4 + 4, dtype=torch.float32, device=dev)
             self.ws_dwhh = torch.zeros(k.gru_dwhh_tc_workspace(P, DEC_STEPS, B) // 4 + 4, dtype=torch.float32, device=dev)
@@ -312,7 +314,11 @@ class CRVAEEngine:
             k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
                       None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
                       1, ENC_STEPS, B, self.ws_gru_enc)
-            k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
+            if self.proj_mode == "tc3" and self.ws_wgrad_tc_enc is not None:     # tcgen05, reduction split over 16 CTAs
+                k.proj_wgrad_tc(self.enc_gates, self.enc_in_hi, self.enc_in_lo, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0,
+                                self.ws_wgrad_tc_enc)
+            else:
+                k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
         if P > 0:
             if defer:
                 k.gru_dwhh_tc(self.gates, self.ghn, self.hs, self.zlat, 0, g["w_hh"], P, DEC_STEPS, B, self.ws_dwhh)
