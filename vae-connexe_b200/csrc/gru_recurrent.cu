@@ -39,9 +39,14 @@ __global__ void __launch_bounds__(256, 2) gru_fwd_kernel(GruFwdArgs a) {
     float* Wt = smem;                 // [H][WT_LD]   Wt[k][g] = W_hh[g][k]
     float* hT = smem + H * WT_LD;     // [H][HT_LD]   hT[k][b] = h[b][k]
 
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    // 16-row tiles (RB == 1, the latency-bound P = 1 shapes): lanes run over the ROWS and a warp holds only two unit
+    // groups, so the W_hh operand of the inner product is a two-address broadcast (96 B per k and warp instead of 768 B:
+    // with lanes over unit groups every warp re-read the whole matrix each step and the step was shared-memory bound).
+    constexpr bool SWAP = (RB == 1);
+    const int tid = threadIdx.x, tx = SWAP ? (tid >> 4) : (tid & 15), ty = SWAP ? (tid & 15) : (tid >> 4);
     const int head = blockIdx.y, b_tile = blockIdx.x * BT;
     const int j0 = 4 * tx;
+    __shared__ float pred_part[SWAP ? 16 * 17 : 1];
 
     const float* __restrict__ W = a.w_hh + (long long)head * G * H;
     for (int e = tid; e < G * H; e += 256) {
@@ -150,8 +155,12 @@ __global__ void __launch_bounds__(256, 2) gru_fwd_kernel(GruFwdArgs a) {
             if (has_lin) {
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) ps = fmaf(hnew[i][jj], wl[jj], ps);
+                if (SWAP) {
+                    pred_part[ty * 17 + tx] = ps;          // the 16 unit groups of a row sit in 8 different warps: sum after the barrier
+                } else {
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+                    for (int o = 8; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+                }
             }
             if (gb < a.B) {
                 float* gdst = a.gates + (row0 + gb) * G + j0;
@@ -161,10 +170,16 @@ __global__ void __launch_bounds__(256, 2) gru_fwd_kernel(GruFwdArgs a) {
                 *reinterpret_cast<float4*>(a.ghn + (row0 + gb) * H + j0) = make_float4(gn[i][0], gn[i][1], gn[i][2], gn[i][3]);
                 *reinterpret_cast<float4*>(a.hs + (row0 + gb) * H + j0) =
                     make_float4(hnew[i][0], hnew[i][1], hnew[i][2], hnew[i][3]);
-                if (has_lin && tx == 0) a.pred[row0 + gb] = ps + blin;
+                if (!SWAP && has_lin && tx == 0) a.pred[row0 + gb] = ps + blin;
             }
         }
         __syncthreads();
+        if (SWAP && has_lin && tid < 16 && b_tile + tid < a.B) {
+            float ps = 0.f;
+#pragma unroll
+            for (int x = 0; x < 16; ++x) ps += pred_part[tid * 17 + x];
+            a.pred[row0 + b_tile + tid] = ps + blin;       // pred_part is rewritten only after the next step's first barrier
+        }
     }
 }
 
@@ -198,7 +213,7 @@ __global__ void __launch_bounds__(256, DEFER_DW ? 2 : 1) gru_bwd_kernel(GruBwdAr
     float* Ds = Ws + G * H;                  // [BT][D_LD]  dgh tile, row-major in b
     float* Hp = Ds + BT * D_LD;              // [BT][HP_LD] h_{t-1} tile
 
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // (the forward's row-lane mapping for 16-row tiles does not pay here: 82 vs 85 us)
     const int head = blockIdx.y, tile = blockIdx.x, b_tile = tile * BT;
     const int j0 = 4 * tx;       // pointwise / matmul-1 column group
     const int g0 = 12 * ty;      // matmul-2 row group (dW_hh rows), columns k = j0..j0+3
