@@ -278,7 +278,8 @@ class CRVAEEngine:
         """Gradient of smooth = loss + ridge + beta*KL (:489/:515) into the grad arena (:497)."""
         k, th, g, B, P, p_ = self.k, self.theta, self.grad, self.B, self.P, self.p
         # decoder BPTT.  With enough heads the dW_hh accumulation is deferred to one tcgen05 GEMM per head
-        # (crvae_gru_dwhh_tc, issued below next to the projection weight gradient): half the FFMA work, 2 CTAs per SM.
+        # (crvae_gru_dwhh_tc, issued below next to the projection weight gradient); the BPTT itself runs on tcgen05
+        # (crvae_gru_bwd_tc) when the rank holds >= 8 heads, else on the exact FFMA2 kernels.
         defer = P >= 8 and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
         if P > 0 and defer and self.rec_mode == "tc3" and hasattr(k, "gru_bwd_tc"):
             k.gru_bwd_tc(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None,
