@@ -103,19 +103,15 @@ def test_autograd_function_api_matches_reference_golden(step):
     assert abs(float(loss) - float(step["loss"])) < TOL * float(step["loss"])
     assert abs(float(mmd) - float(step["kl"])) < TOL * float(step["kl"])
     assert abs(float(ridge) - float(step["ridge"])) < TOL * float(step["ridge"])
-    (loss + float(step["beta"]) * mmd).backward()
+    (loss + ridge + float(step["beta"]) * mmd).backward()
     names = [n for n, _ in m.named_parameters()]
     assert names[:8] == ["gru_left.weight_ih_l0", "gru_left.weight_hh_l0", "gru_left.bias_ih_l0", "gru_left.bias_hh_l0",
                          "fc_mu.weight", "fc_mu.bias", "fc_std.weight", "fc_std.bias"]
     assert names[8:14] == ["networks.0.gru.weight_ih_l0", "networks.0.gru.weight_hh_l0", "networks.0.gru.bias_ih_l0",
                            "networks.0.gru.bias_hh_l0", "networks.0.linear.weight", "networks.0.linear.bias"]
-    # ridge is added analytically by the fused trainer; here it was outside the graph, so compare lam_ridge-free grads
+    # ridge_regularize is wired into autograd too: the full reference gradient (incl. 2*lam_ridge*W) must arrive
     g = _engine_tensors(m.engine.grad)
-    lr_ = float(step["lam_ridge"])
-    exp_whh = step["grad.w_hh"] - 2 * lr_ * step["init.w_hh"]
-    exp_wlin = step["grad.w_lin"] - 2 * lr_ * step["init.w_lin"]
-    assert _rel(g["w_hh"], exp_whh) < TOL and _rel(g["w_lin"], exp_wlin) < TOL
-    for k in ("w_ih", "b_ih", "b_hh", "b_lin", "enc_w_ih", "enc_w_hh", "enc_b_ih", "enc_b_hh", "mu_w", "mu_b", "std_w", "std_b"):
+    for k in O.PARAM_KEYS:
         assert _rel(g[k], step["grad." + k]) < TOL, k
     # reference-style GD + our prox_update on every head, then GC
     for prm_ in m.parameters():
@@ -244,6 +240,55 @@ def test_host_fed_iteration_equals_device_fed(traj):
             assert slot == 5
         finals.append((m.engine.theta.flat.clone(), losses))
     assert torch.equal(finals[0][0], finals[1][0]) and finals[0][1] == finals[1][1]
+
+
+def test_host_fed_changing_batch_equals_eager(traj):
+    """iterate_from_host with a DIFFERENT window batch every step (the minibatch-feeding use, CR-CS-RAE.py:557-558): the
+    update must use the batch its forward ran on.  Compared bit-for-bit against eager update -> bind -> forward, and
+    one iteration against the CPU oracle (gradients of the first host-fed update on the first batch)."""
+    import vae_connexe_b200 as V
+    p, B = 10, 256
+    wins = O.arrange_input(torch.from_numpy(traj["data"].T.copy()), 20)[0]
+    rng = np.random.RandomState(5)
+    Xs = [wins[rng.randint(len(wins), size=B)].contiguous().pin_memory() for _ in range(6)]
+    gen = torch.Generator().manual_seed(3)
+    eps_h = torch.randn(6, B, H, generator=gen).pin_memory()
+    finals = []
+    for host_fed in (False, True):
+        torch.manual_seed(0)
+        m = V.CRVAE(p, np.ones((p, p)), 64)
+        run = V.Phase1Runner(m, Xs[0].cuda(), 5e-2, 0.1, 0.0, 0.1, use_graphs=host_fed)
+        run.forward(eps_h[0].cuda())
+        if host_fed:
+            snap = m.engine.snapshot()
+            run.update(); run.forward(eps_h[0].cuda()); run.capture()       # capture needs one eager pass
+            m.engine.restore(snap); run.forward(eps_h[0].cuda())
+        losses = []
+        for k in range(1, 6):
+            if host_fed:
+                slot = run.iterate_from_host(Xs[k], eps_h[k])
+            else:
+                run.update(); m.engine.bind_batch(Xs[k].cuda()); run.forward(eps_h[k].cuda())
+                losses.append(float(m.engine.loss))
+        if host_fed:
+            ring = run.losses_from_host()
+            losses = [float(ring[i]) for i in range(5)]
+        finals.append((m.engine.theta.flat.clone(), losses))
+    assert torch.equal(finals[0][0], finals[1][0]) and finals[0][1] == finals[1][1]
+    # and the trajectory is the oracle's: 5 iterations, batch k bound before forward k
+    torch.manual_seed(0)
+    m = V.CRVAE(p, np.ones((p, p)), 64)
+    prm = O.params_from_state_dict({k: v.cpu() for k, v in m.state_dict().items()}, np.ones((p, p)))
+    for k in range(5):
+        O.phase1_iteration(prm, Xs[k], eps_h[k], 5e-2, 0.1, 0.0, 0.1)
+    post = _engine_tensors(Arena_from_flat(m.engine, finals[1][0]))
+    for k in O.PARAM_KEYS:
+        assert _rel(post[k], prm[k]) < TOL, k
+
+
+def Arena_from_flat(eng, flat):
+    """Views of a parameter-arena snapshot with the engine's field layout."""
+    return {k: flat[eng.theta.offsets[k]:eng.theta.offsets[k] + int(np.prod(s))].view(*s) for k, s in eng.theta.shapes.items()}
 
 
 def test_p4_train_phase1_tracks_golden_log(traj):

@@ -106,13 +106,16 @@ def test_reference_style_autograd_loop(cpu_backend, step):
     pred, mu, log_var = crvae(X)
     loss = sum([loss_fn(pred[i][:, :, 0], X[:, 10:, i]) for i in range(p)])
     mmd = (-0.5 * (1 + log_var - mu ** 2 - torch.exp(log_var)).sum(dim=-1).sum(dim=0)).mean(dim=0)
-    smooth = loss + beta * mmd
+    ridge = sum([V.ridge_regularize(net, lam_ridge) for net in crvae.networks])        # :488, in the autograd graph
+    smooth = loss + ridge + beta * mmd
     assert abs(float(loss) - float(step["loss"])) < 1e-5 and abs(float(mmd) - float(step["kl"])) < 1e-5
     _ = crvae(X)                      # a later forward (like the check block's :522) must not corrupt the backward
+    _ = crvae(torch.randn_like(X))    # ... nor a later forward on ANOTHER batch (the engine is re-bound behind the node)
     smooth.backward()
     g = crvae.engine.grad
     assert _rel(g["w_ih"], step["grad.w_ih"]) < 1e-5 and _rel(g["enc_w_ih"], step["grad.enc_w_ih"]) < 1e-5
     assert _rel(g["b_hh"], step["grad.b_hh"]) < 1e-5
+    assert _rel(g["w_hh"], step["grad.w_hh"]) < 1e-5 and _rel(g["w_lin"], step["grad.w_lin"]) < 1e-5   # incl. 2*lam_ridge*W
     assert _rel(crvae.networks[3].gru.weight_ih_l0.grad, step["grad.w_ih"][3]) < 1e-5
     for param in crvae.parameters():
         param.data -= lr * param.grad
@@ -121,6 +124,39 @@ def test_reference_style_autograd_loop(cpu_backend, step):
     crvae.zero_grad()
     assert float(crvae.engine.grad.flat.abs().sum()) == 0.0
     assert np.array_equal(crvae.GC().numpy(), step["GC"])
+
+
+def test_forward_rebinds_fresh_temporaries(cpu_backend):
+    """crvae(X_all[idx]) with a new index draw each call: the temporaries usually share an address, so a pointer-keyed
+    bind cache would silently reuse the previous batch.  Every call must see its own batch."""
+    import vae_connexe_b200 as V
+    p = 4
+    torch.manual_seed(0)
+    crvae = V.CRVAE(p, np.ones((p, p)), 64)
+    X_all = torch.randn(50, 20, p)
+    outs = []
+    for rep in range(2):
+        torch.manual_seed(1)                                   # same noise for every call
+        outs.append([])
+        for idx in (torch.arange(0, 8), torch.arange(8, 16), torch.arange(0, 8)):
+            torch.manual_seed(1)
+            pred, _, _ = crvae(X_all[idx])
+            outs[rep].append(torch.stack(pred).detach().clone())
+    a, b, c = outs[0]
+    assert torch.equal(a, c) and not torch.equal(a, b)
+    assert all(torch.equal(x, y) for x, y in zip(outs[0], outs[1]))
+    # deepcopy keeps the subclass (CR-CS-RAE's prior) and the reference's parameter order
+    import copy
+    from vae_connexe_b200 import cs as CS
+    torch.manual_seed(0)
+    m = CS.CRVAE(p, np.ones((p, p)), 64, 3, 0.1)
+    names = [n for n, _ in m.named_parameters()]
+    assert names[8:10] == ["prior.mu", "prior.logvar"] and names[10].startswith("networks.0.")      # CR-CS-RAE.py:259-271
+    st = torch.get_rng_state()
+    m2 = copy.deepcopy(m)
+    assert torch.equal(torch.get_rng_state(), st)
+    assert type(m2) is CS.CRVAE and m2.lambda_cs == 0.1 and torch.equal(m2.prior.flat, m.prior.flat)
+    assert m2.prior.flat.data_ptr() != m.prior.flat.data_ptr()
 
 
 def test_train_phase1_tracks_reference_log(cpu_backend, traj):

@@ -23,7 +23,7 @@ from .modules import CRVAE as _BaseCRVAE
 class GMMPrior(nn.Module):
     """Learnable isotropic Gaussian mixture prior with equal weights (:107-121), stored in a small arena."""
 
-    def __init__(self, K: int, latent_dim: int, device):
+    def __init__(self, K: int, latent_dim: int, device, _init: bool = True):
         super().__init__()
         self.K, self.latent_dim = K, latent_dim
         self.flat = torch.zeros(2 * K * latent_dim, dtype=torch.float32, device=device)
@@ -33,8 +33,9 @@ class GMMPrior(nn.Module):
         self.logvar = nn.Parameter(self.flat[n:].view(K, latent_dim))
         self.mu.grad = self.gflat[:n].view(K, latent_dim)
         self.logvar.grad = self.gflat[n:].view(K, latent_dim)
-        with torch.no_grad():
-            self.mu.copy_(torch.randn(K, latent_dim) * 0.05)      # :114, drawn on the CPU default generator
+        if _init:
+            with torch.no_grad():
+                self.mu.copy_(torch.randn(K, latent_dim) * 0.05)      # :114, drawn on the CPU default generator
 
     @property
     def var(self):
@@ -49,12 +50,27 @@ class CRVAE(_BaseCRVAE):
 
     def __init__(self, num_series, connection, hidden, K, lambda_cs, **kw):
         self._K = int(K)
+        self._prior_holder = []
         super().__init__(num_series, connection, hidden, **kw)
         self.lambda_cs = lambda_cs
 
     def _init_extra(self):
-        # declaration order of CR-CS-RAE.py (:259-271): gru_left, fc_mu, fc_std, PRIOR, then the heads
-        self.prior = GMMPrior(self._K, _H, self.device)
+        # declaration order of CR-CS-RAE.py (:259-271): gru_left, fc_mu, fc_std, PRIOR, then the heads -- the prior's
+        # randn draw happens here (after the encoder's init draws, before the heads'); the module itself is registered
+        # by _register_extra so that parameters() keeps the reference's order
+        self._prior_holder.append(GMMPrior(self._K, _H, self.device))
+
+    def _register_extra(self):
+        if not self._prior_holder:          # _init=False (deepcopy): no generator draw
+            self._prior_holder.append(GMMPrior(self._K, _H, self.device, _init=False))
+        self.prior = self._prior_holder[0]
+
+    def _clone_args(self):
+        return super()._clone_args() + (self._K, self.lambda_cs)
+
+    def _copy_extra_to(self, new):
+        new.prior.flat.copy_(self.prior.flat)
+        new.prior.gflat.copy_(self.prior.gflat)
 
 
 class CSPhase1Runner:

@@ -97,6 +97,7 @@ class CRVAEEngine:
         import os as _os
         self.rec_mode = "tc3" if (_os.environ.get("CRVAE_REC_MODE", "tc3") == "tc3" and hasattr(self.k, "gru_fwd_tc") and P >= 8) else "exact"
         self.B = None
+        self.bind_serial = 0             # bumped by every bind_batch: lets autograd nodes detect a re-bound batch
         self.kl_form = L.KL_SWAPPED
         self._side = None
         self.use_side_stream = True
@@ -111,6 +112,7 @@ class CRVAEEngine:
         assert X.dim() == 3 and X.shape[2] == self.p and X.shape[1] == ENC_STEPS + DEC_STEPS
         X = X.to(self.device, torch.float32)
         B = X.shape[0]
+        self.bind_serial += 1
         lo, hi = self.head_off, self.head_off + self.P
         if self.B != B:
             self._alloc(B)

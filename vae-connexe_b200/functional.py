@@ -39,13 +39,50 @@ def regularize(network, lam):
     return lam * torch.sum(eng.col_norm[i])
 
 
+class _RidgeFn(torch.autograd.Function):
+    """Value by the sumsq kernel; backward adds d/dW = 2*lam*W (times the incoming gradient) into the head's slices
+    of the gradient arena (== linear.weight.grad / gru.weight_hh_l0.grad), so `(loss + ridge + ...).backward()` written
+    like the reference trainer (:488-497) trains the ridge term too."""
+
+    @staticmethod
+    def forward(ctx, anchor, network, lam):
+        eng, i = _head(network)
+        out = torch.zeros(2, dtype=torch.float32, device=eng.device)
+        eng.k.sumsq(eng.theta["w_lin"][i:i + 1], _H, out[0:1])
+        eng.k.sumsq(eng.theta["w_hh"][i:i + 1], _G * _H, out[1:2])
+        ctx.network, ctx.lam = network, float(lam)
+        return lam * (out[0] + out[1])
+
+    @staticmethod
+    def backward(ctx, gout):
+        eng, i = _head(ctx.network)
+        owner = ctx.network._owner[0]
+        alpha = 2.0 * ctx.lam * float(gout)
+        if alpha != 0.0:
+            # The fused BPTT WRITES the gradient arena (it does not accumulate) and autograd does not order the two
+            # nodes: if the model's backward has not run yet in this pass, the addition is queued and applied at its end.
+            if owner._bwd_ran:
+                apply_ridge_grad(eng, i, alpha)
+            else:
+                owner._ridge_pending.append((i, alpha))
+        return None, None, None
+
+
+def apply_ridge_grad(eng, i, alpha):
+    eng.k.axpy(eng.grad["w_hh"][i:i + 1], eng.theta["w_hh"][i:i + 1], _G * _H, alpha)
+    eng.k.axpy(eng.grad["w_lin"][i:i + 1], eng.theta["w_lin"][i:i + 1], _H, alpha)
+
+
 def ridge_regularize(network, lam):
-    """lam * (||linear.weight||^2 + ||weight_hh_l0||^2) (:321-325)."""
-    eng, i = _head(network)
-    out = torch.zeros(2, dtype=torch.float32, device=eng.device)
-    eng.k.sumsq(eng.theta["w_lin"][i:i + 1], _H, out[0:1])
-    eng.k.sumsq(eng.theta["w_hh"][i:i + 1], _G * _H, out[1:2])
-    return lam * (out[0] + out[1])
+    """lam * (||linear.weight||^2 + ||weight_hh_l0||^2) (:321-325), differentiable (see _RidgeFn)."""
+    owner = network._owner[0]
+    if torch.is_grad_enabled() and lam != 0:
+        return _RidgeFn.apply(owner._anchor, network, lam)
+    return _RidgeFn.forward(_NoCtx(), None, network, lam)
+
+
+class _NoCtx:
+    pass
 
 
 def restore_parameters(model, best_model):

@@ -80,9 +80,9 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path) or os.environ.get("CRVAE_REBUILD"):
-        path = _build.build()
+    # build() is a cheap source-digest compare when the library is up to date; it rebuilds a stale one (sources or the
+    # header edited since) and falls back to the shipped binary where there is no nvcc
+    path = _build.build(force=bool(os.environ.get("CRVAE_REBUILD")))
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)     # AttributeError here = header/library mismatch

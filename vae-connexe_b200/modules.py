@@ -81,7 +81,9 @@ class _TrainFn(torch.autograd.Function):
         eng = owner.engine
         eng.forward(eps_dev)
         owner._fwd_serial += 1
+        owner._bwd_ran = False
         ctx.owner, ctx.serial, ctx.eps = owner, owner._fwd_serial, eng.eps.clone()
+        ctx.bound_X, ctx.bind_serial = owner._bound_X, eng.bind_serial     # the batch these activations belong to
         B = eng.B
         lat = eng.lat.clone()
         return eng.pred[:eng.P].clone(), lat[:, _H:].reshape(1, B, _H), lat[:, :_H].reshape(1, B, _H)
@@ -90,7 +92,11 @@ class _TrainFn(torch.autograd.Function):
     def backward(ctx, dpred, dlog_var, dmu):
         owner = ctx.owner
         eng = owner.engine
-        if owner._fwd_serial != ctx.serial:      # activations were overwritten by a later forward
+        if owner._fwd_serial != ctx.serial or eng.bind_serial != ctx.bind_serial:
+            # activations were overwritten by a later forward and / or another batch was bound since: recompute on
+            # the batch and the noise this graph node was built from
+            if eng.bind_serial != ctx.bind_serial:
+                owner._bind(ctx.bound_X)
             eng.forward(ctx.eps)
             owner._fwd_serial += 1
         B = eng.B
@@ -105,6 +111,11 @@ class _TrainFn(torch.autograd.Function):
             extra[:, _H:] = dlog_var.reshape(B, _H)
         eng.backward(beta=0.0, lam_ridge=0.0, dlat_extra=extra)
         owner._sync_ragged_grads()
+        from .functional import apply_ridge_grad
+        for i, alpha in owner._ridge_pending:          # ridge_regularize nodes that ran before this one
+            apply_ridge_grad(eng, i, alpha)
+        owner._ridge_pending.clear()
+        owner._bwd_ran = True
         return None, None, None
 
 
@@ -146,11 +157,14 @@ class CRVAE(nn.Module):
                                    g["enc_w_ih"], g["enc_w_hh"], g["enc_b_ih"], g["enc_b_hh"])
         self.fc_mu = _LinearParams(th["lat_w"][:_H], th["lat_b"][:_H], g["lat_w"][:_H], g["lat_b"][:_H])
         self.fc_std = _LinearParams(th["lat_w"][_H:], th["lat_b"][_H:], g["lat_w"][_H:], g["lat_b"][_H:])
+        self._register_extra()    # hook: modules a variant declares between fc_std and the heads (parameters() order)
         self.networks = nn.ModuleList([GRU(self, i) for i in range(hi - lo)])
         self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
         self._fwd_serial = 0
-        self._bound = None
+        self._bound_X = None
         self._pinned = None
+        self._bwd_ran = False
+        self._ridge_pending = []
 
     # ------------------------------------------------------------------ init / state
     def _init_like_reference(self, full_mask, lo, hi):
@@ -182,6 +196,15 @@ class CRVAE(nn.Module):
                 th[name].copy_(val)
 
     def _init_extra(self):
+        return None
+
+    def _register_extra(self):
+        return None
+
+    def _clone_args(self):
+        return (self.p, copy.deepcopy(self.connection), self.hidden)
+
+    def _copy_extra_to(self, new):
         return None
 
     def state_dict(self, *args, **kwargs):
@@ -223,6 +246,8 @@ class CRVAE(nn.Module):
 
     def zero_grad(self, set_to_none: bool = False):
         self.engine.zero_grad()            # .grad tensors are views of the grad arena: keep them
+        self._bwd_ran = False
+        self._ridge_pending.clear()
 
     def _sync_ragged_grads(self):
         return None                        # masked-dense: gradients of structural zeros are already masked
@@ -236,18 +261,20 @@ class CRVAE(nn.Module):
     def __deepcopy__(self, memo):
         """deepcopy(crvae) is how the reference snapshots its best model (:547): a device-side copy
         of the fused parameter arena into a fresh engine."""
-        new = CRVAE(self.p, copy.deepcopy(self.connection), self.hidden, self.rank, self.world_size, self.group,
-                    device=str(self.device), _init=False)   # no init draws: the caller's generator is untouched
+        new = type(self)(*self._clone_args(), rank=self.rank, world_size=self.world_size, group=self.group,
+                         device=str(self.device), _init=False)   # no init draws: the caller's generator is untouched
         new.engine.theta.flat.copy_(self.engine.theta.flat)
         new.engine.grad.flat.copy_(self.engine.grad.flat)
+        self._copy_extra_to(new)
         return new
 
     # ------------------------------------------------------------------ forward
     def _bind(self, X: torch.Tensor):
-        key = (X.data_ptr(), tuple(X.shape), X._version)
-        if self._bound != key:
-            self.engine.bind_batch(X)
-            self._bound = key
+        """Always re-bind (one small kernel).  A cache keyed on the tensor's address would be wrong: the caching allocator
+        hands a freshly indexed temporary (crvae(X_all[idx])) the address of the previous one, and the trainers re-bind
+        the engine behind the module's back."""
+        self.engine.bind_batch(X)
+        self._bound_X = X
 
     def _draw_eps(self, B: int) -> torch.Tensor:
         """torch.randn(size=mu.size()) on the CPU default generator (:214), then to the device (:215)."""

@@ -127,9 +127,13 @@ class Phase1Runner:
             st["eps"][j].copy_(eps_host, non_blocking=True)
             st["copied"][j].record(st["copy"])
         cur = torch.cuda.current_stream(dev)
+        # Order matters: the backward of the PREVIOUS forward still reads the batch it was computed on (the weight
+        # gradients multiply dgates by enc_in / dec_in), so the update runs first, THEN the new batch is bound, THEN
+        # the forward -- exactly the reference's order when its loop resamples (CR-CS-RAE.py:557-558 precede the forward).
+        self.run_update()
         cur.wait_event(st["copied"][j])
         self.eng.bind_batch(st["X"][j])
-        self.iterate(st["eps"][j])
+        self.run_forward(st["eps"][j])
         st["consumed"][j].record(cur)
         slot = i % st["loss"].numel()
         st["loss"][slot:slot + 1].copy_(self.eng.loss, non_blocking=True)
