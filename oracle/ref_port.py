@@ -32,9 +32,10 @@ class PortCRVAE(nn.Module):
 
     def forward(self, X):
         Xz = torch.cat((torch.zeros_like(X[:, 0:1, :]), X), 1)                          # :205
-        _, h_t = self.gru_left(Xz[:, 1:11, :], torch.zeros(1, X.shape[0], self.hidden)) # :207-208
+        _, h_t = self.gru_left(Xz[:, 1:11, :], torch.zeros(1, X.shape[0], self.hidden, device=X.device))   # :207-208
         mu, log_var = self.fc_mu(h_t), self.fc_std(h_t)                                 # :210-211
-        z = mu + torch.exp(0.5 * log_var) * torch.randn(size=mu.size())                 # :213-216
+        # the reference draws on the CPU default generator and moves the noise to mu's device (:214-215)
+        z = mu + torch.exp(0.5 * log_var) * torch.randn(size=mu.size()).type_as(mu)     # :213-216
         pred = []
         for i, net in enumerate(self.networks):                                         # :218-219
             Xi = Xz[:, :, self.cols[i]]                                                 # :115

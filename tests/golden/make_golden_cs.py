@@ -56,6 +56,24 @@ def main():
         {k: v for k, v in m.state_dict().items() if not k.startswith("prior")}, conn).items()})
     out["final.prior_mu"], out["final.prior_logvar"] = m.prior.mu.detach().numpy().copy(), m.prior.logvar.detach().numpy().copy()
     out["rng_after"] = torch.get_rng_state().numpy()
+    # (3) the "group-lasso prox sweep over lambda" of BASELINE config 5: the same 11-iteration run for every lambda
+    sweep = [0.05, 0.1, 0.2, 0.5, 1.0]
+    out["sweep_lams"] = np.array(sweep)
+    for i, lam in enumerate(sweep):
+        torch.manual_seed(0); np.random.seed(0)
+        m = ref.CRVAE(p, conn, H, K, 0.1)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ref.train_phase1(m, Xt, context=20, lam=lam, lam_ridge=0.01, lr=5e-2, max_iter=11, check_every=5, batch_size=128,
+                             lambda_cs=0.1)
+        txt = buf.getvalue()
+        out[f"sweep{i}.log_mean"] = np.array([float(x) for x in re.findall(r"Mean Loss = ([-\d.eE+]+)", txt)])
+        out[f"sweep{i}.log_cs"] = np.array([float(x) for x in re.findall(r"CS_Div = ([-\d.eE+]+)", txt)])
+        out[f"sweep{i}.log_usage"] = np.array([float(x) for x in re.findall(r"usage = ([\d.]+)%", txt)])
+        prm = O.params_from_state_dict({k: v for k, v in m.state_dict().items() if not k.startswith("prior")}, conn)
+        out[f"sweep{i}.final_w_ih"] = prm["w_ih"].numpy()
+        out[f"sweep{i}.final_enc_w_hh"] = prm["enc_w_hh"].numpy()
+        out[f"sweep{i}.final_GC"] = m.GC().numpy()
     np.savez_compressed(os.path.join(HERE, "cs_p10.npz"), **out)
     print("wrote cs_p10.npz", out["log_it"], out["log_mean"], out["log_cs"], "clamped", int((cs == 0).sum()))
 

@@ -64,13 +64,19 @@ class CRVAEEngine:
     """Kernel-level implementation of CRVAE.forward(mode='train') (:203-221), the trainer's loss
     (:484-489), backward (:497), GD (:498-499) and prox (:502-504) for a head shard."""
 
-    def __init__(self, p: int, mask: np.ndarray, head_off: int = 0, device="cuda", group=None):
+    def __init__(self, p: int, mask: np.ndarray, head_off: int = 0, device="cuda", group=None, comm=None):
         self.k = L.kernels()
         self.p = int(p)
         self.P = int(mask.shape[0])
         self.head_off = int(head_off)
         self.device = torch.device(device)
         self.group = group
+        # comm: the object that sums dz over the head shards (sharding.TorchComm by default when a group is given; tests
+        # inject their own to emulate the other ranks on one GPU)
+        if comm is None and group is not None:
+            from .sharding import TorchComm
+            comm = TorchComm(group)
+        self.comm = comm
         assert mask.shape == (self.P, self.p)
         self.mask_np = np.ascontiguousarray(mask.astype(bool))
         self.dense = bool(self.mask_np.all())
@@ -297,9 +303,9 @@ class CRVAEEngine:
         side = self._fork()
         with self._on(side):
             # dz = sum over ALL heads of dh0 (every head's h0 is z, :218)
-            if self.group is not None:
+            if self.comm is not None:
                 k.latent_bwd(self.dh0 if P > 0 else None, P, None, None, None, 0.0, self.kl_form, None, self.dz_part, B)
-                torch.distributed.all_reduce(self.dz_part, group=self.group)
+                self._allreduce_dz()
                 k.latent_bwd(None, 0, self.dz_part, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
             else:
                 k.latent_bwd(self.dh0, P, None, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
@@ -334,6 +340,17 @@ class CRVAEEngine:
                 k.axpy(g["w_hh"], th["w_hh"], P * G * H, 2.0 * lam_ridge)
                 k.axpy(g["w_lin"], th["w_lin"], P * H, 2.0 * lam_ridge)
         self._join(side)
+
+    def _allreduce_dz(self):
+        """Sum of dz_part over the head shards (the one data-path collective)."""
+        hook = getattr(self, "_stage_hook", None)
+        if hook is not None:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+        self.comm.allreduce_dz(self.dz_part)
+        if hook is not None:
+            e.record()
+            hook(s, e)
 
     # ------------------------------------------------------------------ update
     def step(self, lr: float, lam: float):
@@ -373,3 +390,7 @@ class CRVAEEngine:
 
     def zero_grad(self):
         self.grad.flat.zero_()
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()

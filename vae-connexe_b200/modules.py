@@ -128,7 +128,7 @@ class CRVAE(nn.Module):
     constructing the same torch modules, so torch.manual_seed(s) gives the reference's weights."""
 
     def __init__(self, num_series, connection, hidden, rank: int = 0, world_size: int = 1, group=None,
-                 device: Optional[str] = None, _init: bool = True):
+                 device: Optional[str] = None, _init: bool = True, comm=None):
         super().__init__()
         _require_hidden(hidden)
         kern = L.kernels()                 # raises without libcrvae_b200.so + a B200: there is no CPU path
@@ -148,7 +148,7 @@ class CRVAE(nn.Module):
         self.head_lo, self.head_hi = lo, hi
         full_mask = (conn != 0).T                       # head i reads column j iff connection[j, i] != 0 (:115, :201)
         self.engine = CRVAEEngine(self.p, full_mask[lo:hi], head_off=lo, device=self.device,
-                                  group=group if world_size > 1 else None)
+                                  group=group if world_size > 1 else None, comm=comm if world_size > 1 else None)
         if _init:
             self._init_like_reference(full_mask, lo, hi)
         eng = self.engine
@@ -262,7 +262,7 @@ class CRVAE(nn.Module):
         """deepcopy(crvae) is how the reference snapshots its best model (:547): a device-side copy
         of the fused parameter arena into a fresh engine."""
         new = type(self)(*self._clone_args(), rank=self.rank, world_size=self.world_size, group=self.group,
-                         device=str(self.device), _init=False)   # no init draws: the caller's generator is untouched
+                         device=str(self.device), _init=False, comm=self.engine.comm)   # no init draws: the caller's generator is untouched
         new.engine.theta.flat.copy_(self.engine.theta.flat)
         new.engine.grad.flat.copy_(self.engine.grad.flat)
         self._copy_extra_to(new)

@@ -21,14 +21,26 @@ def head_range(p: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, hi
 
 
+def _stage_through_host(t: torch.Tensor, group) -> bool:
+    """gloo moves CUDA tensors for all_reduce / broadcast only: other collectives go through the host (this is the
+    two-ranks-on-one-GPU test configuration, tests/gpu_dist_parity.py; NCCL never takes this path)."""
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
 def allgather_rows(local_rows: torch.Tensor, p: int, rank: int, world_size: int, group=None) -> torch.Tensor:
     """Stack every rank's [P_r, ...] row block into the full [p, ...] tensor (GC rows, per-head
     losses, predictions).  Shards may differ by one row, so blocks are padded to the widest."""
     widest = (p + world_size - 1) // world_size
     pad = torch.zeros((widest,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
     pad[: local_rows.shape[0]] = local_rows
-    bufs = [torch.empty_like(pad) for _ in range(world_size)]
-    dist.all_gather(bufs, pad, group=group)
+    if _stage_through_host(pad, group):
+        host = pad.cpu()
+        hb = [torch.empty_like(host) for _ in range(world_size)]
+        dist.all_gather(hb, host, group=group)
+        bufs = [b.to(pad.device) for b in hb]
+    else:
+        bufs = [torch.empty_like(pad) for _ in range(world_size)]
+        dist.all_gather(bufs, pad, group=group)
     out = []
     for r in range(world_size):
         lo, hi = head_range(p, r, world_size)
@@ -39,3 +51,17 @@ def allgather_rows(local_rows: torch.Tensor, p: int, rank: int, world_size: int,
 def allreduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+class TorchComm:
+    """The data-path collective of a head shard (sum of dz = sum_heads dh0 over ranks) through
+    torch.distributed (NCCL over NVLink on the GPU box; capturable in a CUDA graph)."""
+
+    def __init__(self, group):
+        self.group = group
+
+    def allreduce_dz(self, dz_part: torch.Tensor) -> None:
+        dist.all_reduce(dz_part, op=dist.ReduceOp.SUM, group=self.group)
+
+    def close(self) -> None:
+        return None
