@@ -143,6 +143,7 @@ def test_p2_stepwise_teacher_forced(traj):
     for it in range(80):
         eps = torch.randn(B, H, generator=gen)
         _engine_load(eng, prm)
+        pre_w = prm["w_ih"].clone()
         act, ld, grads = O.phase1_iteration(prm, X, eps, lr, lam, 0.0, 0.1)     # prm advances in place
         eng.forward(eps.cuda())
         eng.backward(0.1, 0.0)
@@ -156,12 +157,17 @@ def test_p2_stepwise_teacher_forced(traj):
         for k in O.PARAM_KEYS:
             assert _rel(post[k], prm[k]) < TOL, (it, k)
         nz_ref = torch.norm(prm["w_ih"], dim=1) > 0
-        margin = O.prox_margin(torch.from_numpy(np.asarray(post["w_ih"])) if False else prm["w_ih"], lam, lr)
-        assert torch.equal((m.GC() > 0).cpu(), nz_ref), f"zero pattern differs at step {it}"
+        # threshold margin of THIS update: min over columns of | ||W - lr*g|| - lr*lam | / (lr*lam), on the oracle's
+        # pre-prox weights (near-ties must be visible, not silently flaky)
+        min_margin = min(min_margin, O.prox_margin(pre_w - np.float32(lr) * grads["w_ih"], lam, lr))
+        assert torch.equal((m.GC() > 0).cpu(), nz_ref), f"zero pattern differs at step {it} (min margin so far {min_margin:.3e})"
         if prev_nz is not None:
             flips += int((prev_nz != nz_ref).sum())
         prev_nz = nz_ref
     assert flips > 0, "window must cover active sparsification"
+    print(f"P2: 80 teacher-forced states, {flips} column flips, minimum prox-threshold margin {min_margin:.3e} (relative to lr*lam)")
+    # the decisions compared above were all taken with at least this margin; fp32 rounding of the norm is ~1e-7 relative
+    assert min_margin > 1e-6, f"a column sat within {min_margin:.1e} of the threshold: the comparison above was a coin flip"
 
 
 def test_p3_short_free_running_horizon(traj):
@@ -329,7 +335,14 @@ def test_p5_full_golden_run_lands_on_golden_gc(traj):
     assert np.array_equal(gc.astype(np.int8), traj["final_GC"].astype(np.int8))
     assert hashlib.sha256(np.ascontiguousarray(gc.astype(np.int32)).tobytes()).hexdigest() == str(traj["final_GC_sha256"])
     usage = np.array([r["usage"] for r in log])
-    assert (usage[:20] == traj["log_usage"][:20]).all()                       # the first 1,000 iterations track exactly
+    # Hamming distance between our thresholded GC and the reference's at EVERY check (the golden run stores all 100)
+    ham = np.array([int((r["gc"] != traj["log_gc"][i].astype(np.int8)).sum()) for i, r in enumerate(log)])
+    differing = np.nonzero(ham)[0]
+    print(f"P5: GC identical at {100 - len(differing)}/100 checks; first difference at check {differing[0] if len(differing) else None} "
+          f"(iteration {50 * differing[0] if len(differing) else None}); Hamming distance (edges of 100) at the differing checks: "
+          f"max {ham.max()}, mean {ham[differing].mean() if len(differing) else 0:.2f}; histogram {np.bincount(ham).tolist()}")
+    assert (usage[:20] == traj["log_usage"][:20]).all() and (ham[:20] == 0).all()   # the first 1,000 iterations track exactly
+    assert ham.max() <= 3                                                       # flicker of single near-threshold edges, never a different graph
     assert abs(log[-1]["mean_loss"] - traj["log_loss"][99]) < 2e-2 * traj["log_loss"][99]
 
 
@@ -571,3 +584,175 @@ def test_generic_vrae_full_config4_runs():
         res.append([r["total"] for r in log] + [float(model.engine.theta.flat.double().sum())])
     assert res[0] == res[1]
     assert np.isfinite(res[0]).all() and res[0][1] < res[0][0]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: the configurations VERDICT r1 found untested at engine level
+# ------------------------------------------------------------------------------------------------------------------
+class _InjectComm:
+    """Stands in for the other ranks of a head-sharded run on ONE GPU: the all-reduce of dz adds a fixed tensor (what
+    the other shards would have contributed)."""
+
+    def __init__(self, extra):
+        self.extra = extra
+
+    def allreduce_dz(self, dz_part):
+        dz_part.add_(self.extra)
+
+    def close(self):
+        pass
+
+
+def _shard_params(eng):
+    prm = _engine_tensors(eng.theta)
+    prm = {k: v.clone() for k, v in prm.items()}
+    prm["mask"] = torch.from_numpy(eng.mask_np.copy())
+    return prm
+
+
+def test_p1000_shard_iteration_matches_oracle():
+    """BASELINE config 3 at engine level: p = 1000 series, rank 0 of 8 = a 125-head shard (K = 1000 projection depth, the
+    tcgen05 projection / recurrent / gradient kernels at their production shard shape), one full iteration against the CPU
+    oracle with the other ranks' dz contribution injected."""
+    import vae_connexe_b200 as V
+    p, B, world = 1000, 256, 8
+    gen = torch.Generator().manual_seed(5)
+    extra = torch.randn(B, H, generator=gen) * 1e-3
+    torch.manual_seed(1)
+    m = V.CRVAE(p, np.ones((p, p)), 64, rank=0, world_size=world, comm=_InjectComm(extra.cuda()))
+    eng = m.engine
+    assert eng.P == 125 and eng.rec_mode == "tc3" and eng.proj_mode == "tc3"
+    prm = _shard_params(eng)
+    X = torch.randn(B, 20, p, generator=gen)
+    eps = torch.randn(B, H, generator=gen)
+    eng.bind_batch(X.cuda())
+    eng.forward(eps.cuda())
+    eng.backward(0.1, 0.0)
+    act = O.crvae_forward(prm, X, eps)
+    ld = O.crvae_loss(prm, act, 0.0, 0.1, head_slice=slice(0, 125))
+    grads = O.crvae_backward(prm, act, ld, 0.0, 0.1, dz_extra=extra)
+    assert abs(float(eng.loss) - float(ld["loss"])) < TOL * float(ld["loss"])
+    assert _rel(eng.pred, act["pred"]) < TOL
+    g = _engine_tensors(eng.grad)
+    for k in O.PARAM_KEYS:
+        assert _rel(g[k], grads[k]) < TOL, k
+    eng.step(5e-2, 0.1)
+    O.gd_step(prm, grads, 5e-2)
+    prm["w_ih"] = O.prox_update(prm["w_ih"], 0.1, 5e-2)
+    post = _engine_tensors(eng.theta)
+    for k in O.PARAM_KEYS:
+        assert _rel(post[k], prm[k]) < TOL, k
+    assert torch.equal((eng.column_norms()[:125] > 0).cpu(), torch.norm(prm["w_ih"], dim=1) > 0)
+
+
+def test_phase2_iteration_p100_matches_oracle():
+    """Phase 2 at BASELINE config 2 size (p = 100, B = 256): CRVAE on the pruned Lorenz-96 stencil (ragged heads,
+    transposed-column quirk) + VRAE4E + Adam, two iterations against the CPU oracle."""
+    import vae_connexe_b200 as V
+    from vae_connexe_b200.data import lorenz_96_graph
+    p, B = 100, 256
+    conn = lorenz_96_graph(p)
+    torch.manual_seed(3)
+    cg, vr = V.CRVAE(p, conn, 64), V.VRAE4E(p, 64)
+    prm = O.params_from_state_dict({k: v.cpu() for k, v in cg.state_dict().items()}, conn)
+    vprm = O.vrae_params_from_state_dict({k: v.detach().cpu() for k, v in vr.state_dict().items()})
+    gen = torch.Generator().manual_seed(8)
+    X = torch.randn(B, 20, p, generator=gen)
+    eps = [torch.randn(B, H, generator=gen) for _ in range(4)]
+    run = V.Phase2Runner(cg, vr, X.cuda(), 5e-2, 0.0, 0.0, use_graphs=False)
+    ce, ve = cg.engine, vr.engine
+    adam_state = {}
+    for it in range(2):
+        run.forward(eps[2 * it].cuda(), eps[2 * it + 1].cuda())
+        o = O.phase2_iteration(prm, vprm, adam_state, it + 1, X, eps[2 * it], eps[2 * it + 1], 5e-2)
+        assert abs(float(ce.loss) - float(o["lossd"]["loss"])) < TOL * float(o["lossd"]["loss"])
+        assert abs(float(ce.kl) - float(o["lossd"]["kl"])) < TOL * abs(float(o["lossd"]["kl"]))
+        assert _rel(ce.err_tbp.permute(1, 0, 2), o["err"]) < TOL
+        assert abs(float(ve.loss) - float(o["vloss"]["loss"])) < TOL * float(o["vloss"]["loss"])
+        assert abs(float(ve.kl) - float(o["vloss"]["kl"])) < TOL * abs(float(o["vloss"]["kl"]))
+        run.update()
+        vg, cgr = _vrae_tensors(ve.grad), _engine_tensors(ce.grad)
+        for k in O.VRAE_KEYS:
+            assert _rel(vg[k], o["vgrads"][k]) < TOL, (it, k)
+        for k in O.PARAM_KEYS:
+            assert _rel(cgr[k], o["grads"][k]) < TOL, (it, k)
+        vp, cp = _vrae_tensors(ve.theta), _engine_tensors(ce.theta)
+        for k in O.VRAE_KEYS:
+            assert _rel(vp[k], vprm[k]) < TOL, (it, k)
+        for k in O.PARAM_KEYS:
+            assert _rel(cp[k], prm[k]) < TOL, (it, k)
+    assert float((cp["w_ih"] * (~prm["mask"])[:, None, :].float()).abs().sum()) == 0.0     # structural zeros stay zero
+
+
+def test_generic_vrae_full_config4_matches_oracle():
+    """BASELINE config 4 at FULL size (batch 1024, seq 512, latent 32, D = 10): forward, both losses and every gradient
+    of one iteration against the CPU oracle (512 sequential steps each way)."""
+    from vae_connexe_b200 import vrae as VR
+    torch.manual_seed(4)
+    B, T, D, Z = 1024, 512, 10, 32
+    model = VR.VRAE(D, 64, Z, "gru", "tanh")
+    prm = O.gvrae_params_from_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    data = torch.randn(B, T, D)
+    st = torch.get_rng_state()
+    eps = torch.randn(B, Z)
+    torch.set_rng_state(st)
+    recon, mu, logvar = model(data.cuda())
+    a = O.gvrae_forward(prm, data, eps, "tanh")
+    l = O.gvrae_loss(a, 1.0)
+    assert _rel(recon.permute(1, 0, 2), a["recon"]) < TOL and _rel(mu, a["mu"]) < TOL
+    assert abs(float(model.engine.sse) / B - float(l["rec"])) < TOL * float(l["rec"])
+    assert abs(float(model.engine.kl) - float(l["kld"])) < TOL * float(l["kld"])
+    model.engine.backward(1.0)
+    gr = O.gvrae_backward(prm, a, l, 1.0, "tanh")
+    eg = model.engine.grad
+    for k in ("enc_w_ih", "enc_w_hh", "enc_b_ih", "enc_b_hh", "dec_w_ih", "dec_w_hh", "dec_b_ih", "dec_b_hh", "z2h_w", "z2h_b",
+              "out_w", "out_b"):
+        assert _rel(eg[k], gr[k]) < TOL, k
+
+
+def test_cs_rae_lambda_sweep_tracks_reference(traj):
+    """Config 5's "group-lasso prox sweep over lambda": the reference's CR-CS-RAE trainer was run for every lambda of
+    {0.05, 0.1, 0.2, 0.5, 1.0} (tests/golden/make_golden_cs.py); our trainer must reproduce each run's log, final GC
+    (bit-exact) and weights."""
+    from vae_connexe_b200 import cs as CS
+    g = np.load(os.path.join(GOLDEN, "cs_p10.npz"))
+    Xt = torch.from_numpy(traj["data"].T.copy())[None].cuda()
+    for i, lam in enumerate(g["sweep_lams"]):
+        torch.manual_seed(0); np.random.seed(0)
+        m = CS.CRVAE(10, np.ones((10, 10)), 64, 10, 0.1)
+        log = []
+        CS.train_phase1(m, Xt, context=20, lam=float(lam), lam_ridge=0.01, lr=5e-2, max_iter=11, check_every=5, batch_size=128,
+                        lambda_cs=0.1, verbose=0, log=log)
+        for j, r in enumerate(log):
+            assert abs(r["mean_loss"] - g[f"sweep{i}.log_mean"][j]) < TOL * g[f"sweep{i}.log_mean"][j] + 2e-6, (lam, j)
+            assert abs(r["cs"] - g[f"sweep{i}.log_cs"][j]) < TOL * g[f"sweep{i}.log_cs"][j] + 2e-6, (lam, j)
+            assert r["usage"] == g[f"sweep{i}.log_usage"][j], (lam, j)
+        assert np.array_equal(m.GC().cpu().numpy(), g[f"sweep{i}.final_GC"]), lam
+        assert _rel(m.engine.theta["w_ih"], g[f"sweep{i}.final_w_ih"]) < TOL, lam
+        assert _rel(m.engine.theta["enc_w_hh"], g[f"sweep{i}.final_enc_w_hh"]) < TOL, lam
+
+
+def test_generation_matches_live_reference_fixture():
+    """Test-mode generation against sequences produced by the REFERENCE's own forward(mode='test') (tests/golden/
+    make_golden_gen.py): CRVAE phase 0, VRAE4E, CRVAE phase 1 (fed with the VRAE4E sample), at p = 8 with the shipped
+    weights and at p = 100, B = 256 with the weights re-created from the seed."""
+    import vae_connexe_b200 as V
+    g = np.load(os.path.join(GOLDEN, "gen_p8.npz"))
+    for tag in ("a", "b"):
+        p, B = int(g[f"{tag}.p"]), int(g[f"{tag}.B"])
+        torch.manual_seed(11)
+        m, v = V.CRVAE(p, np.ones((p, p)), 64), V.VRAE4E(p, 64)
+        if tag == "a":
+            sd = m.state_dict()
+            for k in sd:
+                assert np.array_equal(sd[k].cpu().numpy(), g[f"a.crvae.{k}"]), k          # seed parity with the shipped weights
+        gen = torch.Generator().manual_seed(5)
+        X, err = torch.randn(B, 20, p, generator=gen), torch.randn(B, 10, p, generator=gen)
+        n = g[f"{tag}.gen_phase0"].shape[0]
+        torch.manual_seed(21); s0 = m(X.cuda(), mode="test")
+        torch.manual_seed(22); s1 = v(err.cuda(), mode="test")
+        torch.manual_seed(23); s2 = m(X.cuda(), s1[:, 1:], mode="test", phase=1)
+        assert s0.shape == (B, 21, p) and s1.shape == (B, 22, p) and s2.shape == (B, 21, p)
+        assert _rel(s0[:n], g[f"{tag}.gen_phase0"]) < TOL, tag
+        assert _rel(s1[:n], g[f"{tag}.gen_vrae"]) < TOL, tag
+        assert _rel(s2[:n], g[f"{tag}.gen_phase1"]) < TOL, tag

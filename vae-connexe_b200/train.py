@@ -217,9 +217,10 @@ def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0,
         # ---- rest of the check block (:524-547) ------------------------------------------------
         mean_loss = np.float32(np.float32(float(loss_t) + float(ridge_t)) / np.float32(p))   # :530-533
         kl_val = float(eng.kl)
-        usage = None
+        usage = gc_now = None
         if lam > 0:
-            usage = float(100 * torch.mean(crvae.GC().float()))   # :541-542
+            gc_now = crvae.GC()
+            usage = float(100 * torch.mean(gc_now.float()))       # :541-542
         if verbose > 0 and rank0:
             print(('-' * 10 + 'Iter = %d' + '-' * 10) % (it))
             print('Loss = %f' % mean_loss)
@@ -227,7 +228,8 @@ def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0,
             if lam > 0:
                 print('Variable usage = %.2f%%' % usage)
         if log is not None:
-            log.append(dict(it=it, mean_loss=float(mean_loss), kl=kl_val, usage=usage))
+            log.append(dict(it=it, mean_loss=float(mean_loss), kl=kl_val, usage=usage,
+                            gc=None if gc_now is None else gc_now.cpu().numpy().astype(np.int8)))
         if mean_loss < best_loss:                                 # :544-547
             best_loss, best_it = mean_loss, it
             best_snap = eng.snapshot()
