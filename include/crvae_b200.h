@@ -171,6 +171,20 @@ int crvae_gru_bwd_tc(float* gates, float* ghn, const float* hs, const float* h0,
                      const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
                      float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0, int P, int T, int B,
                      void* workspace, void* stream);
+
+/* Low-latency forms of crvae_gru_fwd / crvae_gru_bwd_deferred (same arguments, same results in exact fp32) for the
+ * shapes whose cost is the latency of ONE recurrent step rather than bandwidth: small head shards (p = 100 over 8 GPUs
+ * = 12-13 heads), the replicated encoder (CRVAE_lorenz96.py:208), VRAE4E (:155, :166) and the long sequences of
+ * VRAE.py.  One CTA per (head, 16-row tile); W_hh resident in shared memory; the step's gate / h / gh_n slabs move by
+ * cp.async.bulk through a shared-memory ring (in place: gi -> r|z|n, r|z|n -> dgi), so nothing of the step sits in
+ * the load/store queue; packed fp32 FMAs.  crvae_gru_bwd_ll leaves dw_hh to crvae_gru_dwhh_tc.                       */
+int crvae_gru_fwd_ll(float* gates, const float* b_ih, const float* w_hh, const float* b_hh,
+                     const float* h0, int64_t h0_head_stride, const float* w_lin, const float* b_lin,
+                     float* hs, float* ghn, float* pred, int P, int T, int B, int t_skip, void* stream);
+int crvae_gru_bwd_ll(float* gates, float* ghn, const float* hs, const float* h0, int64_t h0_head_stride,
+                     const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
+                     const float* dhs, float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0,
+                     int P, int T, int B, void* workspace, void* stream);
 size_t crvae_gru_dwhh_tc_workspace(int P, int T, int B);
 int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const float* hs, const float* h0,
                       int64_t h0_head_stride, float* dw_hh, int P, int T, int B, void* workspace, void* stream);

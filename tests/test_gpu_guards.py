@@ -139,6 +139,31 @@ def test_guard_recurrent_exact(P, T, B, tile):
         k.set_batch_tile(0)
 
 
+@pytest.mark.parametrize("P,T,B", [(1, 10, 256), (13, 10, 256), (2, 7, 100), (1, 25, 33), (20, 10, 64)])
+def test_guard_recurrent_low_latency(P, T, B):
+    """The bulk-copy kernels (cp.async.bulk in both directions, slots reused in place): canaries + run-to-run identity."""
+    k = _k()
+    gd = Guarded()
+    gd.add("gates", _rand(P, T, B, G, seed=1))
+    gd.add("b_ih", _rand(P, G, seed=2, scale=0.2)); gd.add("w_hh", _rand(P, G, H, seed=3, scale=0.125))
+    gd.add("b_hh", _rand(P, G, seed=4, scale=0.2)); gd.add("h0", _rand(P, B, H, seed=5))
+    gd.add("w_lin", _rand(P, H, seed=6, scale=0.2)); gd.add("b_lin", _rand(P, seed=7))
+    gd.add("hs", shape=(P, T, B, H)); gd.add("ghn", shape=(P, T, B, H)); gd.add("pred", shape=(P, T, B))
+    fw = _twice(gd, lambda: k.gru_fwd_ll(gd["gates"], gd["b_ih"], gd["w_hh"], gd["b_hh"], gd["h0"], B * H, gd["w_lin"], gd["b_lin"],
+                                         gd["hs"], gd["ghn"], gd["pred"], P, T, B, 0), ("gates", "hs", "ghn", "pred"))
+    gb = Guarded()
+    gb.add("gates", fw["gates"]); gb.add("ghn", fw["ghn"]); gb.add("hs", fw["hs"]); gb.add("h0", gd["h0"].clone())
+    gb.add("w_hh", gd["w_hh"].clone()); gb.add("w_lin", gd["w_lin"].clone()); gb.add("dpred", _rand(P, T, B, seed=8))
+    gb.add("dhs", _rand(P, T, B, H, seed=9, scale=0.1))
+    for n, s in (("db_hh", (P, G)), ("db_ih", (P, G)), ("dw_lin", (P, H)), ("db_lin", (P,)), ("dh0", (P, B, H))):
+        gb.add(n, shape=s)
+    gb.add("ws", shape=(k.gru_bwd_workspace(P, B) // 4 + 4,))
+    for with_dhs in (False, True):
+        _twice(gb, lambda: k.gru_bwd_ll(gb["gates"], gb["ghn"], gb["hs"], gb["h0"], B * H, gb["w_hh"], gb["w_lin"], gb["dpred"], None,
+                                        gb["dhs"] if with_dhs else None, gb["db_hh"], gb["db_ih"], gb["dw_lin"], gb["db_lin"], gb["dh0"],
+                                        P, T, B, gb["ws"]), ("gates", "ghn", "db_hh", "db_ih", "dw_lin", "db_lin", "dh0"))
+
+
 @pytest.mark.parametrize("P,T,B,K,t_skip", [(2, 10, 256, 100, 1), (3, 4, 40, 36, 1), (1, 10, 256, 12, 0), (5, 10, 129, 1000, 1), (2, 10, 96, 260, 1)])
 def test_guard_projection_tensor_core(P, T, B, K, t_skip):
     k = _k()

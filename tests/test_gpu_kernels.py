@@ -187,6 +187,66 @@ def test_gru_forward_tensor_core(P, T, B, lin, t_skip, shared_h0):
         assert _rel(out[name], ref[name]) < 2e-5, (name, _rel(out[name], ref[name]))
 
 
+@pytest.mark.parametrize("P,T,B,lin,t_skip,shared_h0,last,with_dhs", [
+    (1, 10, 256, False, 0, False, True, False),      # the encoder (gru_left, :208): gradient enters through h_T only
+    (13, 10, 256, True, 1, True, False, False),      # a 13-head decoder shard (p = 100 over 8 GPUs): h0 = z shared
+    (20, 10, 256, True, 1, True, False, False),      # 320 CTAs > 148 SMs: the two-CTAs-per-SM ring depths
+    (2, 10, 100, True, 1, False, False, False),      # ragged last tile (4 of 16 rows)
+    (1, 25, 33, True, 0, True, True, True),          # long sequence (ring wraps many times), ragged, per-step dhs (VRAE.py decoder)
+    (3, 1, 16, True, 0, False, False, False),        # a single step
+    (2, 2, 48, False, 2, False, True, False),        # every step is a zero-input step
+])
+def test_gru_low_latency_forward_backward(P, T, B, lin, t_skip, shared_h0, last, with_dhs):
+    """crvae_gru_fwd_ll / crvae_gru_bwd_ll (16-row tiles, bulk-copy slab ring, packed fp32 FMAs) against the CPU oracle,
+    and to fp32 rounding against the exact FFMA kernels they stand in for."""
+    k, o = _k(), OracleKernels()
+    gi = _rand(P, T, B, G, seed=1)
+    b_ih, w_hh, b_hh = _rand(P, G, seed=2, scale=0.2), _rand(P, G, H, seed=3, scale=0.125), _rand(P, G, seed=4, scale=0.2)
+    h0 = _rand(B, H, seed=5) if shared_h0 else _rand(P, B, H, seed=5)
+    stride = 0 if shared_h0 else B * H
+    w_lin, b_lin = (_rand(P, H, seed=6, scale=0.2), _rand(P, seed=7)) if lin else (None, None)
+    c = lambda t: None if t is None else t.cuda()
+    ref = dict(g=gi.clone(), hs=torch.zeros(P, T, B, H), ghn=torch.zeros(P, T, B, H), pred=torch.zeros(P, T, B) if lin else None)
+    o.gru_fwd(ref["g"], b_ih, w_hh, b_hh, h0, stride, w_lin, b_lin, ref["hs"], ref["ghn"], ref["pred"], P, T, B, t_skip)
+    outs = []
+    for fn in (k.gru_fwd_ll, k.gru_fwd):
+        out = dict(g=gi.clone().cuda(), hs=torch.zeros(P, T, B, H, device="cuda"), ghn=torch.zeros(P, T, B, H, device="cuda"),
+                   pred=torch.zeros(P, T, B, device="cuda") if lin else None)
+        fn(out["g"], c(b_ih), c(w_hh), c(b_hh), c(h0), stride, c(w_lin), c(b_lin), out["hs"], out["ghn"], out["pred"], P, T, B, t_skip)
+        torch.cuda.synchronize()
+        outs.append(out)
+    ll, ex = outs
+    for name in ("g", "hs", "ghn") + (("pred",) if lin else ()):
+        assert _rel(ll[name], ref[name]) < 2e-5, (name, _rel(ll[name], ref[name]))
+    # exact fp32 on both sides; the low-latency kernel sums k in two fixed halves, so agreement is to rounding, not bit-for-bit
+    assert _rel(ll["hs"], ex["hs"]) < 2e-6 and _rel(ll["g"], ex["g"]) < 2e-6 and _rel(ll["ghn"], ex["ghn"]) < 2e-6
+    # ---- backward on the forward's outputs ----
+    dpred = _rand(P, T, B, seed=8) if lin else None
+    dh_last = _rand(P, B, H, seed=9, scale=0.1) if last else None
+    dhs = _rand(P, T, B, H, seed=10, scale=0.1) if with_dhs else None
+    z = lambda *s: torch.zeros(*s)
+    rb = dict(g=ref["g"].clone(), dw_hh=z(P, G, H), db_hh=z(P, G), db_ih=z(P, G), dw_lin=z(P, H) if lin else None,
+              db_lin=z(P) if lin else None, dh0=z(P, B, H))
+    o.gru_bwd(rb["g"], ref["ghn"], ref["hs"], h0, stride, w_hh, w_lin, dpred, dh_last, dhs, rb["dw_hh"], rb["db_hh"], rb["db_ih"],
+              rb["dw_lin"], rb["db_lin"], rb["dh0"], P, T, B, None)
+    gpu = {n: (None if v is None else torch.zeros_like(v).cuda()) for n, v in rb.items()}
+    gpu["g"] = ll["g"].clone()
+    ghn = ll["ghn"].clone()
+    ws = torch.zeros(k.gru_bwd_workspace(P, B) // 4 + 4, device="cuda")
+    k.gru_bwd_ll(gpu["g"], ghn, ll["hs"], c(h0), stride, c(w_hh), c(w_lin), c(dpred), c(dh_last), c(dhs), gpu["db_hh"], gpu["db_ih"],
+                 gpu["dw_lin"], gpu["db_lin"], gpu["dh0"], P, T, B, ws)
+    torch.cuda.synchronize()
+    for name in ("g", "db_hh", "db_ih", "dw_lin", "db_lin", "dh0"):
+        if rb[name] is not None:
+            assert _rel(gpu[name], rb[name]) < 5e-5, (name, _rel(gpu[name], rb[name]))
+    assert _rel(ghn, rb["g"][..., 2 * H:] * ref["g"][..., :H]) < 5e-5          # dgh_n = dgi_n * r left in the ghn buffer
+    if B % 32 == 0:
+        ws2 = torch.zeros(k.gru_dwhh_tc_workspace(P, T, B) // 4 + 4, device="cuda")
+        k.gru_dwhh_tc(gpu["g"], ghn, ll["hs"], c(h0), stride, gpu["dw_hh"], P, T, B, ws2)
+        torch.cuda.synchronize()
+        assert _rel(gpu["dw_hh"], rb["dw_hh"]) < 5e-5
+
+
 @pytest.mark.parametrize("P,T,B,lin,shared_h0,last", [(3, 10, 256, True, True, False), (2, 5, 64, False, False, True),
                                                        (20, 10, 256, True, True, False), (1, 10, 32, True, True, True),
                                                        (2, 3, 300, True, False, True), (1, 1, 128, True, True, False)])

@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import lib as L
+from . import rec as R
 
 H = 64
 G = 3 * H
@@ -100,8 +101,15 @@ class CRVAEEngine:
             self.enc_w_hi, self.enc_w_lo = zl(self.theta["enc_w_ih"]), zl(self.theta["enc_w_ih"])
         # recurrence mode: "tc3" = tcgen05 gate GEMM (crvae_gru_fwd_tc, 3xTF32; default once a rank holds enough heads
         # to fill the SMs with 128-row tiles), "exact" = persistent fp32 FFMA kernel (CRVAE_REC_MODE=exact, small shards)
+        # "ll" = low-latency 16-row tiles (crvae_gru_fwd_ll / _bwd_ll): shards of few heads, where one step's latency is the cost
         import os as _os
-        self.rec_mode = "tc3" if (_os.environ.get("CRVAE_REC_MODE", "tc3") == "tc3" and hasattr(self.k, "gru_fwd_tc") and P >= 8) else "exact"
+        want = _os.environ.get("CRVAE_REC_MODE", "auto")
+        if R.has_ll(self.k) and P > 0 and (want == "ll" or (want == "auto" and P <= R.LL_MAX_HEADS)):
+            self.rec_mode = "ll"
+        elif want in ("auto", "tc3") and hasattr(self.k, "gru_fwd_tc") and P >= 8:
+            self.rec_mode = "tc3"
+        else:
+            self.rec_mode = "exact"
         self.B = None
         self.bind_serial = 0             # bumped by every bind_batch: lets autograd nodes detect a re-bound batch
         self.kl_form = L.KL_SWAPPED
@@ -183,6 +191,8 @@ class CRVAEEngine:
         self.ws_lat = None
         if hasattr(k, "latent_head_fwd"):
             self.ws_lat = torch.zeros(k.latent_head_workspace(B) // 4 + 4, dtype=torch.float32, device=dev)
+        n = R.dwhh_workspace(k, 1, ENC_STEPS, B)
+        self.ws_dwhh_enc = torch.zeros(n, dtype=torch.float32, device=dev) if n else None
         self.ws_wgrad_tc = self.ws_dwhh = self.ws_wgrad_tc_enc = None
         if hasattr(k, "proj_wgrad_tc_workspace"):
             self.ws_wgrad_tc_enc = torch.zeros(k.proj_wgrad_tc_workspace(1, ENC_STEPS, B, self.p, 0) // 4 + 4, dtype=torch.float32, device=dev)
@@ -204,8 +214,8 @@ class CRVAEEngine:
         with self._on(side):
             # encoder GRU (gru_left, :208) -> h_T
             self._project(self.enc_in, "enc", th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, ENC_STEPS, 0)
-            k.gru_fwd(self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
-                      self.enc_hs, self.enc_ghn, None, 1, ENC_STEPS, B, 0)
+            R.gru_forward_small(k, self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
+                                self.enc_hs, self.enc_ghn, None, 1, ENC_STEPS, B, 0)
             hT = self.enc_hs[0, ENC_STEPS - 1]
             # [mu | log_var] = h_T [fc_mu ; fc_std]^T + b (:210-211); z = mu + exp(.5 lv) eps (:213-216); KL (:486)
             if self.ws_lat is not None:     # fused: one launch instead of GEMM + pointwise on the latency-bound chain
@@ -221,6 +231,9 @@ class CRVAEEngine:
             if self.rec_mode == "tc3":
                 k.gru_fwd_tc(self.gates, th["b_ih"], th["w_hh"], None, th["b_hh"], self.zlat, 0, th["w_lin"],
                              th["b_lin"], self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
+            elif self.rec_mode == "ll":
+                k.gru_fwd_ll(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
+                             self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
             else:
                 k.gru_fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
                           self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
@@ -288,8 +301,11 @@ class CRVAEEngine:
         # decoder BPTT.  With enough heads the dW_hh accumulation is deferred to one tcgen05 GEMM per head
         # (crvae_gru_dwhh_tc, issued below next to the projection weight gradient); the BPTT itself runs on tcgen05
         # (crvae_gru_bwd_tc) when the rank holds >= 8 heads, else on the exact FFMA2 kernels.
-        defer = P >= 8 and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
-        if P > 0 and defer and self.rec_mode == "tc3" and hasattr(k, "gru_bwd_tc"):
+        defer = (P >= 8 or self.rec_mode == "ll") and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
+        if P > 0 and defer and self.rec_mode == "ll":
+            k.gru_bwd_ll(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
+                         g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
+        elif P > 0 and defer and self.rec_mode == "tc3" and hasattr(k, "gru_bwd_tc"):
             k.gru_bwd_tc(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None,
                          g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
         elif P > 0 and defer:
@@ -320,9 +336,9 @@ class CRVAEEngine:
                 k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
                 k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
             # encoder BPTT: gradient enters only through h_T
-            k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
-                      None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
-                      1, ENC_STEPS, B, self.ws_gru_enc)
+            R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
+                                 None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
+                                 1, ENC_STEPS, B, self.ws_gru_enc, self.ws_dwhh_enc)
             if self.proj_mode == "tc3" and self.ws_wgrad_tc_enc is not None:     # tcgen05, reduction split over 16 CTAs
                 k.proj_wgrad_tc(self.enc_gates, self.enc_in_hi, self.enc_in_lo, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0,
                                 self.ws_wgrad_tc_enc)

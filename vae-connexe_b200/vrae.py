@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import lib as L
+from . import rec as R
 from .engine import Arena, G, H
 
 _ACT = {"tanh": 0, "sigmoid": 1, "relu": 2}
@@ -58,6 +59,8 @@ class _Engine:
             self.ones_B, self.ones_TB = torch.ones(B, 1, device=dev), torch.ones(T * B, 1, device=dev)
             k = self.k
             self.ws_gru = torch.zeros(k.gru_bwd_workspace(1, B) // 4 + 4, dtype=torch.float32, device=dev)
+            n = R.dwhh_workspace(k, 1, T, B)
+            self.ws_dwhh = torch.zeros(n, dtype=torch.float32, device=dev) if n else None
             self.ws_wgrad = torch.zeros(k.proj_wgrad_workspace(1, T, B, D) // 4 + 4, dtype=torch.float32, device=dev)
         self.xin.copy_(x.transpose(0, 1))
 
@@ -66,16 +69,16 @@ class _Engine:
         k, th, B, T, D, Z = self.k, self.theta, self.B, self.T, self.D, self.Z
         self.eps.copy_(eps.reshape(B, Z), non_blocking=True)
         k.proj_fwd(self.xin, th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, T, B, D, 0)
-        k.gru_fwd(self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
-                  self.enc_hs, self.enc_ghn, None, 1, T, B, 0)                                                  # :30
+        R.gru_forward_small(k, self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
+                            self.enc_hs, self.enc_ghn, None, 1, T, B, 0)                                        # :30
         hT = self.enc_hs[0, T - 1]
         k.gemm(L.GEMM_NT, 1, B, 2 * Z, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * Z, 0, th["lat_b"], 0)        # :34-35
         k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, L.KL_STANDARD, Z)                                # :117-121, :144
         k.gemm(L.GEMM_NT, 1, B, H, Z, self.zlat, Z, 0, th["z2h_w"], Z, 0, self.pre0, H, 0, th["z2h_b"], 0)
         k.tanh_fwd(self.pre0, self.h0, B * H)                                                                    # :72
         k.proj_fwd(self.xin, th["dec_w_ih"], th["dec_b_ih"], self.dec_gates, 1, T, B, D, 0)                      # input of step t = x[:, t]
-        k.gru_fwd(self.dec_gates, th["dec_b_ih"], th["dec_w_hh"], th["dec_b_hh"], self.h0, 0, None, None,
-                  self.dec_hs, self.dec_ghn, None, 1, T, B, 0)                                                  # :85-89
+        R.gru_forward_small(k, self.dec_gates, th["dec_b_ih"], th["dec_w_hh"], th["dec_b_hh"], self.h0, 0, None, None,
+                            self.dec_hs, self.dec_ghn, None, 1, T, B, 0)                                        # :85-89
         k.gemm(L.GEMM_NT, 1, T * B, D, H, self.dec_hs, H, 0, th["out_w"], H, 0, self.pre, D, 0, th["out_b"], 0)
         k.act_fwd(self.pre, self.recon, T * B * D, self.act)                                                     # :91
         # rec_loss = SSE / batch (:143): sse over everything, d(recon) = 2*(recon - x)/B
@@ -88,8 +91,9 @@ class _Engine:
         k.gemm(L.GEMM_TN, 1, D, H, TB, self.dpre, D, 0, self.dec_hs, H, 0, g["out_w"], H, 0)
         k.gemm(L.GEMM_TN, 1, 1, D, TB, self.ones_TB, 1, 0, self.dpre, D, 0, g["out_b"], D, 0)
         k.gemm(L.GEMM_NN, 1, TB, H, D, self.dpre, D, 0, th["out_w"], H, 0, self.dhs, H, 0)
-        k.gru_bwd(self.dec_gates, self.dec_ghn, self.dec_hs, self.h0, 0, th["dec_w_hh"], None, None, None, self.dhs,
-                  g["dec_w_hh"].view(1, G, H), g["dec_b_hh"], g["dec_b_ih"], None, None, self.dh0, 1, T, B, self.ws_gru)
+        R.gru_backward_small(k, self.dec_gates, self.dec_ghn, self.dec_hs, self.h0, 0, th["dec_w_hh"], None, None, None, self.dhs,
+                             g["dec_w_hh"].view(1, G, H), g["dec_b_hh"], g["dec_b_ih"], None, None, self.dh0, 1, T, B, self.ws_gru,
+                             self.ws_dwhh)
         k.proj_wgrad(self.dec_gates, self.xin, None, g["dec_w_ih"], 1, T, B, D, 0, self.ws_wgrad)
         k.tanh_bwd(self.dh0, self.h0, self.dpre0, B * H)
         k.gemm(L.GEMM_TN, 1, H, Z, B, self.dpre0, H, 0, self.zlat, Z, 0, g["z2h_w"], Z, 0)
@@ -100,8 +104,9 @@ class _Engine:
         k.gemm(L.GEMM_TN, 1, 2 * Z, H, B, self.dlat, 2 * Z, 0, hT, H, 0, g["lat_w"], H, 0)
         k.gemm(L.GEMM_TN, 1, 1, 2 * Z, B, self.ones_B, 1, 0, self.dlat, 2 * Z, 0, g["lat_b"], 2 * Z, 0)
         k.gemm(L.GEMM_NN, 1, B, H, 2 * Z, self.dlat, 2 * Z, 0, th["lat_w"], H, 0, self.dhT, H, 0)
-        k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT, None,
-                  g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0, 1, T, B, self.ws_gru)
+        R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT, None,
+                             g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0, 1, T, B, self.ws_gru,
+                             self.ws_dwhh)
         k.proj_wgrad(self.enc_gates, self.xin, None, g["enc_w_ih"], 1, T, B, D, 0, self.ws_wgrad)
 
     def adam_step(self, lr: float):

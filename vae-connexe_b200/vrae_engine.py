@@ -14,6 +14,7 @@ from typing import Optional
 import torch
 
 from . import lib as L
+from . import rec as R
 from .engine import Arena, G, H
 
 STEPS = 10    # VRAE4E sees the 10-step residual (:152-155, :166)
@@ -60,6 +61,8 @@ class VRAE4EEngine:
         k = self.k
         self.ws_lat = torch.zeros(k.latent_head_workspace(B) // 4 + 4, dtype=torch.float32, device=dev) if hasattr(k, "latent_head_fwd") else None
         self.ws_gru = torch.zeros(k.gru_bwd_workspace(1, B) // 4 + 4, dtype=torch.float32, device=dev)
+        n = R.dwhh_workspace(k, 1, STEPS, B)
+        self.ws_dwhh = torch.zeros(n, dtype=torch.float32, device=dev) if n else None
         self.ws_wgrad = torch.zeros(k.proj_wgrad_workspace(1, STEPS, B, p_) // 4 + 4, dtype=torch.float32, device=dev)
 
     def bind_error(self, err_tbp: torch.Tensor):
@@ -76,8 +79,8 @@ class VRAE4EEngine:
         if eps is not None:
             self.eps.copy_(eps.reshape(B, H), non_blocking=True)
         k.proj_fwd(self.enc_in, th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, STEPS, B, p_, 0)
-        k.gru_fwd(self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
-                  self.enc_hs, self.enc_ghn, None, 1, STEPS, B, 0)
+        R.gru_forward_small(k, self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
+                            self.enc_hs, self.enc_ghn, None, 1, STEPS, B, 0)
         hT = self.enc_hs[0, STEPS - 1]
         if self.ws_lat is not None:      # fused fc_mu|fc_std + reparameterisation + KL (:157-163), one launch
             k.latent_head_fwd(hT, th["lat_w"], th["lat_b"], self.eps, self.lat, self.zlat, self.kl, B, self.kl_form, self.ws_lat)
@@ -87,8 +90,8 @@ class VRAE4EEngine:
         k.gemm(L.GEMM_NT, 1, B, H, H, self.zlat, H, 0, th["hid_w"], H, 0, self.pre, H, 0, th["hid_b"], 0)       # :164
         k.tanh_fwd(self.pre, self.zh, B * H)
         k.proj_fwd(self.dec_in, th["dec_w_ih"], th["dec_b_ih"], self.dec_gates, 1, STEPS, B, p_, 1)
-        k.gru_fwd(self.dec_gates, th["dec_b_ih"], th["dec_w_hh"], th["dec_b_hh"], self.zh, 0, None, None,
-                  self.dec_hs, self.dec_ghn, None, 1, STEPS, B, 1)                                              # :166
+        R.gru_forward_small(k, self.dec_gates, th["dec_b_ih"], th["dec_w_hh"], th["dec_b_hh"], self.zh, 0, None, None,
+                            self.dec_hs, self.dec_ghn, None, 1, STEPS, B, 1)                                    # :166
         k.gemm(L.GEMM_NT, 1, STEPS * B, p_, H, self.dec_hs, H, 0, th["out_w"], H, 0, self.pred, p_, 0, th["out_b"], 0)  # :167
         k.mse_fwd_bwd(self.pred, self.enc_in, self.sse, self.dpred, None, 1, STEPS, B * p_)                     # :601
         k.dot_small(self.sse, 1, 1.0 / (STEPS * B * p_), self.loss)
@@ -103,8 +106,9 @@ class VRAE4EEngine:
         k.gemm(L.GEMM_TN, 1, p_, H, TB, self.dpred, p_, 0, self.dec_hs, H, 0, g["out_w"], H, 0)
         k.gemm(L.GEMM_TN, 1, 1, p_, TB, self.ones_TB, 1, 0, self.dpred, p_, 0, g["out_b"], p_, 0)
         k.gemm(L.GEMM_NN, 1, TB, H, p_, self.dpred, p_, 0, th["out_w"], H, 0, self.dhs, H, 0)
-        k.gru_bwd(self.dec_gates, self.dec_ghn, self.dec_hs, self.zh, 0, th["dec_w_hh"], None, None, None, self.dhs,
-                  g["dec_w_hh"].view(1, G, H), g["dec_b_hh"], g["dec_b_ih"], None, None, self.dzh, 1, STEPS, B, self.ws_gru)
+        R.gru_backward_small(k, self.dec_gates, self.dec_ghn, self.dec_hs, self.zh, 0, th["dec_w_hh"], None, None, None, self.dhs,
+                             g["dec_w_hh"].view(1, G, H), g["dec_b_hh"], g["dec_b_ih"], None, None, self.dzh, 1, STEPS, B, self.ws_gru,
+                             self.ws_dwhh)
         k.proj_wgrad(self.dec_gates, self.dec_in, None, g["dec_w_ih"], 1, STEPS, B, p_, 1, self.ws_wgrad)
         k.tanh_bwd(self.dzh, self.zh, self.dpre, B * H)
         k.gemm(L.GEMM_TN, 1, H, H, B, self.dpre, H, 0, self.zlat, H, 0, g["hid_w"], H, 0)
@@ -120,8 +124,9 @@ class VRAE4EEngine:
             k.gemm(L.GEMM_TN, 1, 2 * H, H, B, self.dlat, 2 * H, 0, hT, H, 0, g["lat_w"], H, 0)
             k.gemm(L.GEMM_TN, 1, 1, 2 * H, B, self.ones_B, 1, 0, self.dlat, 2 * H, 0, g["lat_b"], 2 * H, 0)
             k.gemm(L.GEMM_NN, 1, B, H, 2 * H, self.dlat, 2 * H, 0, th["lat_w"], H, 0, self.dhT, H, 0)
-        k.gru_bwd(self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT, None,
-                  g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0, 1, STEPS, B, self.ws_gru)
+        R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT, None,
+                             g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0, 1, STEPS, B, self.ws_gru,
+                             self.ws_dwhh)
         k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, STEPS, B, p_, 0, self.ws_wgrad)
 
     def adam_step(self, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
