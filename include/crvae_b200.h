@@ -259,6 +259,13 @@ int crvae_act_fwd(const float* x, float* y, int64_t n, int kind, void* stream);
 int crvae_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int kind, void* stream);
 /* out[c][r] = in[r][c]: residual [P][T*B] (head-major) <-> [T*B][P] (VRAE4E input, :599/:639)       */
 int crvae_transpose(const float* in, float* out, int rows, int cols, void* stream);
+/* Test-mode generation (CRVAE.forward(mode='test'), CRVAE_lorenz96.py:223-243 / :264-284), the step between two
+ * recurrent updates: every head's next input is the vector of ALL heads' outputs (:232-236).  y [R][W][B] = the step's
+ * outputs gathered over R head shards of at most W heads (balanced contiguous partition: the first `rem` shards hold
+ * base+1 heads, the others base; one GPU: R = 1, base = W = p, rem = 0).  Writes x_next [B][p] = y (+ scale*noise[b][t][j],
+ * phase 1, :281-283), the stored sequence out [B][steps][p] at step t, and (optional) the tf32 hi / lo split of x_next.   */
+int crvae_gen_scatter(const float* y, const float* noise, float* x, float* x_hi, float* x_lo, float* out, int B, int p,
+                      int t, int steps, int base, int rem, int widest, float scale, void* stream);
 
 /* Same update with the step count in device memory (step = *step_counter + 1, then incremented):
  * lets the whole phase-2 iteration be replayed from a CUDA graph.                                  */

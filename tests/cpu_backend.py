@@ -215,6 +215,23 @@ class OracleKernels:
         dst.reshape(-1)[: rows * cols].view(cols, rows).copy_(src.reshape(-1)[: rows * cols].view(rows, cols).t())
         self.launches += 1
 
+    def gen_scatter(self, y, noise, x, x_hi, x_lo, out, B, p, t, steps, base, rem, widest, scale):
+        yv = y.reshape(-1, widest, B)
+        cols = []
+        for j in range(p):
+            if j < rem * (base + 1):
+                r, l = divmod(j, base + 1)
+            else:
+                r, l = divmod(j - rem * (base + 1), base)
+                r += rem
+            cols.append(yv[r, l])
+        v = torch.stack(cols, 1)                                   # [B, p]
+        if noise is not None:
+            v = v + torch.tensor(scale, dtype=torch.float32) * noise[:, t, :]
+        x.reshape(B, p).copy_(v)
+        out[:, t, :] = v
+        self.launches += 1
+
     def sumsq(self, x, n, out):
         out[0] = (x.reshape(-1)[:n] ** 2).sum()
         self.launches += 1

@@ -61,6 +61,13 @@ def main():
                     ok = False; print(f"[rank {rank}] phase {phase} log mismatch", key, a, b)
         if phase == 1 and not torch.equal(ms.GC(), m1.GC()):
             ok = False; print(f"[rank {rank}] GC mismatch")
+        if phase == 1:      # test-mode generation on the head shard (per-step all-gather of the heads' outputs) == single GPU
+            Xg = torch.zeros(32, 20, 10, device="cuda")
+            torch.manual_seed(5); ga = ms(Xg, mode="test")
+            torch.manual_seed(5); gb = m1(Xg, mode="test")
+            relg = float((ga - gb).abs().max() / gb.abs().max())
+            if ga.shape != (32, 21, 10) or relg > 1e-5:
+                ok = False; print(f"[rank {rank}] sharded generation mismatch {relg:.2e}")
         sd1 = m1.state_dict()
         for k, t in ms.state_dict().items():
             rel = float((t - sd1[k]).abs().max() / sd1[k].abs().max().clamp_min(1e-30))

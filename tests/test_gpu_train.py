@@ -756,3 +756,26 @@ def test_generation_matches_live_reference_fixture():
         assert _rel(s0[:n], g[f"{tag}.gen_phase0"]) < TOL, tag
         assert _rel(s1[:n], g[f"{tag}.gen_vrae"]) < TOL, tag
         assert _rel(s2[:n], g[f"{tag}.gen_phase1"]) < TOL, tag
+
+
+def test_check_block_generation_flag(traj):
+    """generate_in_check=True materialises the check block's test-mode sample (:550) without touching the training
+    trajectory or the generator state: same log, same weights, same torch RNG end state as with the flag off; the sample
+    equals a stand-alone generation from the same h_0 on the same weights."""
+    import vae_connexe_b200 as V
+    from vae_connexe_b200.generate import crvae_generate
+    Xt = torch.from_numpy(traj["data"].T.copy())[None].cuda()
+    res = []
+    for flag in (False, True):
+        torch.manual_seed(0); np.random.seed(0)
+        m = V.CRVAE(10, np.ones((10, 10)), 64)
+        log = []
+        V.train_phase1(m, Xt, context=20, lam=0.1, lam_ridge=0, lr=5e-2, max_iter=51, check_every=50, verbose=0, log=log,
+                       generate_in_check=flag)
+        res.append((m, log, torch.get_rng_state().clone()))
+    (m0, log0, st0), (m1, log1, st1) = res
+    assert torch.equal(st0, st1) and torch.equal(m0.engine.theta.flat, m1.engine.theta.flat)
+    assert [r["mean_loss"] for r in log0] == [r["mean_loss"] for r in log1]
+    s = m1.last_sample
+    assert s.shape == (256, 21, 10) and bool(torch.isfinite(s).all()) and float(s.abs().max()) > 0
+    assert not hasattr(m0, "last_sample")

@@ -436,6 +436,46 @@ extern "C" int crvae_tanh_bwd(const float* dy, const float* y, float* dx, int64_
     return check_launch("tanh_bwd_kernel");
 }
 
+namespace crvae {
+// Test-mode generation, the step between two recurrent updates (CRVAE_lorenz96.py:232-236, :281-283): the p heads' scalar
+// outputs of this step become the next input row of EVERY head.  y [R][W][B]: outputs gathered over R head shards of at
+// most W heads each (balanced contiguous partition: the first `rem` shards hold base+1 heads, the rest base); one pass
+// writes x_next[b][j] = y_j[b] (+ scale * noise[b][t][j]), the stored sequence out[b][t][j], and the tf32 hi / lo split
+// of x_next for the tensor-core projection of the next step.
+__global__ void gen_scatter_kernel(const float* __restrict__ y, const float* __restrict__ noise, float* __restrict__ x,
+                                   float* __restrict__ x_hi, float* __restrict__ x_lo, float* __restrict__ out, int B, int p, int t,
+                                   int steps, int base, int rem, int widest, float scale) {
+    const long long n = (long long)B * p;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(e / p), j = (int)(e - (long long)b * p);
+        int r, l;
+        if (j < rem * (base + 1)) { r = j / (base + 1); l = j - r * (base + 1); }
+        else { const int jj = j - rem * (base + 1); r = rem + jj / base; l = jj - (r - rem) * base; }
+        float v = y[((long long)r * widest + l) * B + b];
+        if (noise) v = __fadd_rn(v, __fmul_rn(scale, noise[((long long)b * steps + t) * p + j]));
+        x[e] = v;
+        out[((long long)b * steps + t) * p + j] = v;
+        if (x_hi) {
+            uint32_t hi;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+            x_hi[e] = __uint_as_float(hi);
+            x_lo[e] = __fsub_rn(v, __uint_as_float(hi));
+        }
+    }
+}
+
+}  // namespace crvae
+
+extern "C" int crvae_gen_scatter(const float* y, const float* noise, float* x, float* x_hi, float* x_lo, float* out, int B, int p,
+                                 int t, int steps, int base, int rem, int widest, float scale, void* stream) {
+    CRVAE_REQUIRE(y && x && out && B > 0 && p > 0 && t >= 0 && t < steps && base >= 0 && rem >= 0 && widest > 0, "bad argument");
+    CRVAE_REQUIRE((x_hi == nullptr) == (x_lo == nullptr), "x_hi and x_lo go together");
+    CRVAE_REQUIRE(base > 0 || rem * (base + 1) >= p, "partition does not cover the p heads");
+    gen_scatter_kernel<<<grid_for((long long)B * p), 256, 0, (cudaStream_t)stream>>>(y, noise, x, x_hi, x_lo, out, B, p, t, steps, base, rem,
+                                                                                  widest, scale);
+    return check_launch("gen_scatter_kernel");
+}
+
 extern "C" int crvae_transpose(const float* in, float* out, int rows, int cols, void* stream) {
     CRVAE_REQUIRE(in && out && rows > 0 && cols > 0, "bad argument");
     transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, rows, cols);

@@ -199,8 +199,13 @@ int tc_splits_for(int P, int tiles_per_head, int nchunks, int ctas_per_sm) {
     // the SM count without spilling into a second wave
     int s = (148 * ctas_per_sm) / (P * tiles_per_head);
     if (s < 1) s = 1;
-    if (s > nchunks) s = nchunks;
     if (s > 16) s = 16;
+    // accuracy: the tensor core accumulates in fp32 WITHOUT round-to-nearest, so one accumulator chain drifts by about
+    // 2^-24 per MMA K-step (measured: 32,768 rows in one chain = 2.3e-4 relative, all entries low).  Chains are kept to
+    // 256 chunks of 16 rows (512 K-steps, ~3e-5); the partial sums are added in fp32 round-to-nearest by split_sum_kernel.
+    const int s_acc = (nchunks + 255) / 256;
+    if (s < s_acc) s = s_acc;
+    if (s > nchunks) s = nchunks;
     return s;
 }
 int launch_split_sum(const float* ws, float* out, int P, int S, long long n, cudaStream_t st) {
@@ -213,7 +218,7 @@ int launch_split_sum(const float* ws, float* out, int P, int S, long long n, cud
 
 extern "C" size_t crvae_proj_wgrad_tc_workspace(int P, int T, int B, int K, int t_skip) {
     const int R = (T - t_skip) * B;
-    const int S = tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK, 1);
+    const int S = min(tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK, 1), 64);      // gridDim.z <= 64
     return S > 1 ? (size_t)P * S * CRVAE_G * K * sizeof(float) : 16;
 }
 
@@ -241,7 +246,7 @@ extern "C" int crvae_proj_wgrad_tc(const float* dgates, const float* x_hi, const
         if (e != cudaSuccess) { set_error("proj_wgrad_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    const int S = tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK, 1);
+    const int S = min(tc_splits_for(P, (K + WG_BM - 1) / WG_BM, (R + WG_BK - 1) / WG_BK, 1), 64);      // gridDim.z <= 64
     if (S > 1) CRVAE_REQUIRE(workspace && aligned16(workspace), "workspace required (crvae_proj_wgrad_tc_workspace)");
     WgradTcArgs a{S > 1 ? (float*)workspace : dw_ih, mask, K, R, t_skip * B, S};
     dim3 grid((K + WG_BM - 1) / WG_BM, P, S);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "crvae_act_fwd": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_int, _c_void_p]),
     "crvae_act_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_int, _c_void_p]),
     "crvae_transpose": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "crvae_gen_scatter": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_float, _c_void_p]),
     "crvae_sumsq": (_c_int, [_c_void_p, _c_i64, _c_void_p, _c_void_p]),
     "crvae_dot_small": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p]),
     "crvae_axpy": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_float, _c_void_p]),
@@ -284,6 +285,10 @@ class Kernels:
 
     def transpose(self, src, dst, rows, cols):
         self._ck(self.lib.crvae_transpose(ptr(src), ptr(dst), rows, cols, stream_ptr()), "crvae_transpose")
+
+    def gen_scatter(self, y, noise, x, x_hi, x_lo, out, B, p, t, steps, base, rem, widest, scale):
+        self._ck(self.lib.crvae_gen_scatter(ptr(y), ptr(noise), ptr(x), ptr(x_hi), ptr(x_lo), ptr(out), B, p, t, steps, base, rem,
+                                            widest, float(scale), stream_ptr()), "crvae_gen_scatter")
 
     def sumsq(self, x, n, out):
         self._ck(self.lib.crvae_sumsq(ptr(x), n, ptr(out), stream_ptr()), "crvae_sumsq")

@@ -165,9 +165,11 @@ def _planned_draws(max_iter: int, check_every: int) -> int:
 
 def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0,
                  lookback=5, check_every=50, verbose=1, sparsity=100, batch_size=256,
-                 use_graphs=True, log: Optional[List[dict]] = None):
-    """Phase-1 trainer, same signature as the reference (:457-458) (+ two keyword-only extras:
-    use_graphs, log).  X: (n_series, T, p) fp32 on the model's device.  Returns the (always
+                 use_graphs=True, log: Optional[List[dict]] = None, generate_in_check: bool = False):
+    """Phase-1 trainer, same signature as the reference (:457-458) (+ keyword-only extras: use_graphs, log,
+    generate_in_check = also materialise the check block's test-mode sample (:550-555; the reference computes it,
+    min-max scales it and throws it away -- off by default, its noise draw is consumed either way; when on, the last
+    sample is left in crvae.last_sample).  X: (n_series, T, p) fp32 on the model's device.  Returns the (always
     empty, :463/:560) train_loss_list; the model is left at its best checkpoint (:558)."""
     p = X.shape[-1]
     eng = crvae.engine
@@ -194,7 +196,7 @@ def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0,
             continue
         if check:
             eps_check = feed.next()                               # :522 draw
-            feed.next()                                           # :550 -> :225 generation draw (output unused)
+            h0_gen = feed.next()                                  # :550 -> :225 generation draw
         run.run_update()                                          # :497-506
         if check:
             # The check-block forward (:522) and the training forward (:508) use the same weights,
@@ -214,6 +216,9 @@ def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0,
             captured = True
         if not check:
             continue
+        if generate_in_check:                                     # :550 (one CUDA-graph replay, generate.py)
+            from .generate import crvae_generate
+            crvae.last_sample = crvae_generate(crvae, Xb, phase=0, h0=h0_gen)
         # ---- rest of the check block (:524-547) ------------------------------------------------
         mean_loss = np.float32(np.float32(float(loss_t) + float(ridge_t)) / np.float32(p))   # :530-533
         kl_val = float(eng.kl)
