@@ -259,6 +259,23 @@ int crvae_act_fwd(const float* x, float* y, int64_t n, int kind, void* stream);
 int crvae_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int kind, void* stream);
 /* out[c][r] = in[r][c]: residual [P][T*B] (head-major) <-> [T*B][P] (VRAE4E input, :599/:639)       */
 int crvae_transpose(const float* in, float* out, int rows, int cols, void* stream);
+/* Gather-packed ragged heads (phase 2: head i = GRU(k_i, H) on the k_i series selected by column i of the connection
+ * matrix, CRVAE_lorenz96.py:115, :200-201, :788-790).  w_ih [P,G,Kp] packed (Kp = widest head's input count rounded up
+ * to 4), cols [P,Kp] int32 = series index of every packed column (ascending), mask [P,Kp] u8 = 0 on padding columns.
+ *   crvae_gather_cols        xg[i][r][c] = mask[i][c] ? x[r][cols[i][c]] : 0         (x [rows,K] -> xg [P,rows,Kp])
+ *   crvae_proj_fwd_packed    gates[i] = b_ih[i] + xg[i] . w_ih[i]^T                  (exact fp32)
+ *   crvae_proj_wgrad_packed  dw_ih[i] = dgates[i]^T . xg[i], padding columns zeroed  (exact fp32)
+ * Results equal the masked-dense form (crvae_proj_fwd / crvae_proj_wgrad on [P,G,K_dense] with structural zeros) BIT
+ * FOR BIT: ascending packed columns = the dense sum without its exact zeros; the gradient's reduction is cut into
+ * the number of splits the dense form uses for K_dense series.                                                   */
+int crvae_gather_cols(const float* x, const int* cols, const uint8_t* mask, float* xg, int P, int64_t rows, int K,
+                      int Kp, void* stream);
+int crvae_proj_fwd_packed(const float* xg, const float* w_ih, const float* b_ih, float* gates,
+                          int P, int T, int B, int Kp, int t_skip, void* stream);
+size_t crvae_proj_wgrad_packed_workspace(int P, int T, int B, int Kp, int K_dense);
+int crvae_proj_wgrad_packed(const float* dgates, const float* xg, const uint8_t* mask, float* dw_ih,
+                            int P, int T, int B, int Kp, int K_dense, int t_skip, void* workspace, void* stream);
+
 /* Test-mode generation (CRVAE.forward(mode='test'), CRVAE_lorenz96.py:223-243 / :264-284), the step between two
  * recurrent updates: every head's next input is the vector of ALL heads' outputs (:232-236).  y [R][W][B] = the step's
  * outputs gathered over R head shards of at most W heads (balanced contiguous partition: the first `rem` shards hold

@@ -68,6 +68,33 @@ class OracleKernels:
         dw_ih.reshape(P, G, K).copy_(dw)
         self.launches += 1
 
+    # -- gather-packed ragged heads -----------------------------------------------------------------
+    def gather_cols(self, x, cols, mask, xg, P, rows, K, Kp):
+        xv = x.reshape(rows, K)
+        g = xv[:, cols.long().reshape(P, Kp)]                      # [rows, P, Kp]
+        g = g.permute(1, 0, 2)
+        if mask is not None:
+            g = g * mask.reshape(P, 1, Kp).to(g.dtype)
+        xg.reshape(-1)[: P * rows * Kp].view(P, rows, Kp).copy_(g)
+        self.launches += 1
+
+    def proj_fwd_packed(self, xg, w_ih, b_ih, gates, P, T, B, Kp, t_skip):
+        w = w_ih.reshape(P, G, Kp); x = xg.reshape(P, T, B, Kp)
+        gi = torch.einsum("ptbk,pgk->ptbg", x[:, t_skip:], w) + b_ih.reshape(P, 1, 1, G)
+        gates.reshape(-1)[: P * T * B * G].view(P, T, B, G)[:, t_skip:] = gi
+        self.launches += 1
+
+    def proj_wgrad_packed_workspace(self, P, T, B, Kp, K_dense):
+        return 16
+
+    def proj_wgrad_packed(self, dgates, xg, mask, dw_ih, P, T, B, Kp, K_dense, t_skip, ws):
+        dg = dgates.reshape(-1)[: P * T * B * G].view(P, T, B, G); x = xg.reshape(P, T, B, Kp)
+        dw = torch.einsum("ptbg,ptbk->pgk", dg[:, t_skip:], x[:, t_skip:])
+        if mask is not None:
+            dw = dw * mask.reshape(P, 1, Kp).to(dw.dtype)
+        dw_ih.reshape(P, G, Kp).copy_(dw)
+        self.launches += 1
+
     # -- recurrence ------------------------------------------------------------------------------
     def gru_fwd(self, gates, b_ih, w_hh, b_hh, h0, h0_stride, w_lin, b_lin, hs, ghn, pred, P, T, B, t_skip):
         gv = gates.reshape(-1)[: P * T * B * G].view(P, T, B, G)

@@ -779,3 +779,78 @@ def test_check_block_generation_flag(traj):
     s = m1.last_sample
     assert s.shape == (256, 21, 10) and bool(torch.isfinite(s).all()) and float(s.abs().max()) > 0
     assert not hasattr(m0, "last_sample")
+
+
+def test_gather_packed_heads_bitwise_equal_masked_dense_and_oracle():
+    """gather-packed ragged heads (CSR-like per-head column lists, :115 / :200-201) against (i) the exact
+    masked-dense path BIT FOR BIT over several phase-1 iterations with the prox active and a phase-2 iteration pair, and
+    (ii) the CPU oracle; (iii) at p = 1000 on the Lorenz-96 ring (k = 4) the packed first-layer weights take <= 1 % of the
+    dense bytes and an iteration runs."""
+    import vae_connexe_b200 as V
+    from vae_connexe_b200.data import lorenz_96_graph
+    p, B = 40, 64
+    conn = lorenz_96_graph(p)
+    gen = torch.Generator().manual_seed(5)
+    X = torch.randn(B, 20, p, generator=gen)
+    eps = [torch.randn(B, H, generator=gen) for _ in range(6)]
+    runs = []
+    os.environ["CRVAE_PROJ_MODE"] = "exact"                      # the masked-dense comparator on the exact FFMA projection
+    try:
+        for packed in (False, True):
+            torch.manual_seed(3)
+            m = V.CRVAE(p, conn, 64, packed=packed)
+            assert m.engine.packed == packed and m.engine.proj_mode == ("packed" if packed else "exact")
+            r = V.Phase1Runner(m, X.cuda(), 5e-2, 0.05, 0.01, 0.1, use_graphs=False)
+            r.forward(eps[0].cuda())
+            hist = []
+            for k in range(1, 6):
+                r.update(); r.forward(eps[k].cuda())
+                hist.append((float(m.engine.loss), m.engine.unpack_w(m.engine.theta["w_ih"]).clone(), m.engine.theta.flat[m.engine.rest_off:].clone()))
+            runs.append((m, hist))
+    finally:
+        del os.environ["CRVAE_PROJ_MODE"]
+    (md, ha), (pk, hb) = runs
+    assert pk.engine.theta["w_ih"].shape == (p, 192, 4) and tuple(pk.networks[7].gru.weight_ih_l0.shape) == (192, 4)
+    for (la, wa, ra), (lb, wb, rb) in zip(ha, hb):
+        assert la == lb and torch.equal(wa, wb) and torch.equal(ra, rb)
+    assert torch.equal(pk.GC(), md.GC())
+    # (ii) oracle, one iteration from a fresh seed
+    torch.manual_seed(4)
+    m = V.CRVAE(p, conn, 64)                                     # automatic: k = 4 <= p / 4 -> packed
+    assert m.engine.packed
+    prm = O.params_from_state_dict({k: v.cpu() for k, v in m.state_dict().items()}, conn)
+    e = m.engine
+    e.bind_batch(X.cuda()); e.forward(eps[0].cuda()); e.backward(1.0, 0.0)
+    act, ld, grads = O.phase1_iteration(prm, X, eps[0], 5e-2, 0.05, 0.0, 1.0)
+    assert abs(float(e.loss) - float(ld["loss"])) < TOL * float(ld["loss"])
+    g = _engine_tensors({**{k: e.grad[k] for k in e.grad.shapes}, "w_ih": e.unpack_w(e.grad["w_ih"])})
+    for k in O.PARAM_KEYS:
+        assert _rel(g[k], grads[k]) < TOL, k
+    e.step(5e-2, 0.05)
+    assert _rel(e.unpack_w(e.theta["w_ih"]), prm["w_ih"]) < TOL
+    assert torch.equal(m.GC().cpu(), O.gc_matrix(prm["w_ih"]))
+    # phase 2 on packed heads == masked-dense (tensor-core projection there): within tolerance
+    res = []
+    for packed in (False, True):
+        torch.manual_seed(6)
+        c, v = V.CRVAE(p, conn, 64, packed=packed), V.VRAE4E(p, 64)
+        r2 = V.Phase2Runner(c, v, X.cuda(), 5e-2, 0.0, 0.0, use_graphs=packed)
+        r2.forward(eps[0].cuda(), eps[1].cuda()); r2.update(); r2.forward(eps[2].cuda(), eps[3].cuda())
+        if packed:
+            r2.capture()
+        r2.iterate(eps[4].cuda(), eps[5].cuda())
+        res.append((float(c.engine.loss), float(v.engine.loss), c.engine.unpack_w(c.engine.theta["w_ih"]).clone()))
+    assert abs(res[0][0] - res[1][0]) < TOL * abs(res[0][0]) and abs(res[0][1] - res[1][1]) < TOL * abs(res[0][1])
+    assert _rel(res[1][2], res[0][2]) < TOL
+    # (iii) p = 1000 ring graph: footprint and one iteration
+    p3 = 1000
+    torch.manual_seed(1)
+    big = V.CRVAE(p3, lorenz_96_graph(p3), 64)
+    eb = big.engine
+    assert eb.packed and eb.Kw == 4
+    dense_bytes = p3 * 192 * p3 * 4
+    assert eb.theta["w_ih"].numel() * 4 <= 0.01 * dense_bytes and eb.grad["w_ih"].numel() * 4 <= 0.01 * dense_bytes
+    Xb = torch.randn(256, 20, p3, generator=gen)
+    eb.bind_batch(Xb.cuda()); eb.forward(torch.randn(256, H, generator=gen).cuda()); eb.backward(1.0, 0.0); eb.step(5e-2, 0.0)
+    assert np.isfinite(float(eb.loss)) and bool(torch.isfinite(eb.theta.flat).all())
+    assert eb.dec_in_g.numel() * 4 < 0.05 * (10 * 256 * p3 * p3 * 4)          # gathered inputs: Kp columns per head, not p

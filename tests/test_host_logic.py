@@ -159,6 +159,48 @@ def test_forward_rebinds_fresh_temporaries(cpu_backend):
     assert m2.prior.flat.data_ptr() != m.prior.flat.data_ptr()
 
 
+def test_gather_packed_heads_equal_masked_dense(cpu_backend):
+    """Gather-packed ragged heads: same init draws, same forward / gradients / update / GC / state_dict as
+    the masked-dense storage, with (3H, k_i) weight views like the reference's pruned heads (:200-201)."""
+    import vae_connexe_b200 as V
+    from vae_connexe_b200.data import lorenz_96_graph
+    p, B = 16, 24
+    conn = lorenz_96_graph(p)                                     # 4 inputs per head
+    models = []
+    for packed in (False, True):
+        torch.manual_seed(3)
+        models.append(V.CRVAE(p, conn, 64, packed=packed))
+    md, pk = models
+    assert not md.engine.packed and pk.engine.packed and pk.engine.Kw == 4
+    assert pk.engine.theta["w_ih"].shape == (p, 192, 4) and md.engine.theta["w_ih"].shape == (p, 192, p)
+    assert tuple(pk.networks[3].gru.weight_ih_l0.shape) == (192, 4)
+    assert torch.equal(pk.engine.unpack_w(pk.engine.theta["w_ih"]), md.engine.theta["w_ih"])
+    sd_a, sd_b = md.state_dict(), pk.state_dict()
+    assert all(torch.equal(sd_a[k], sd_b[k]) for k in sd_a)
+    gen = torch.Generator().manual_seed(5)
+    X, eps = torch.randn(B, 20, p, generator=gen), torch.randn(B, 64, generator=gen)
+    for m in models:
+        e = m.engine
+        e.bind_batch(X); e.forward(eps); e.backward(1.0, 0.01); e.step(5e-2, 0.05)
+    assert abs(float(md.engine.loss) - float(pk.engine.loss)) < 1e-6
+    assert _rel(pk.engine.unpack_w(pk.engine.grad["w_ih"]), md.engine.grad["w_ih"]) < 1e-6
+    assert _rel(pk.engine.unpack_w(pk.engine.theta["w_ih"]), md.engine.theta["w_ih"]) < 1e-6
+    assert _rel(pk.engine.theta["enc_w_ih"], md.engine.theta["enc_w_ih"]) < 1e-6
+    assert torch.equal(pk.GC(), md.GC())
+    # load_state_dict round trip and deepcopy keep the packed storage
+    import copy
+    pk2 = copy.deepcopy(pk)
+    assert pk2.engine.packed and torch.equal(pk2.engine.theta.flat, pk.engine.theta.flat)
+    torch.manual_seed(9)
+    other = V.CRVAE(p, conn, 64, packed=True)
+    other.load_state_dict(md.state_dict())
+    assert _rel(other.engine.unpack_w(other.engine.theta["w_ih"]), md.engine.theta["w_ih"]) < 1e-7
+    # generation on packed heads == masked-dense
+    torch.manual_seed(1); a = md(X, mode="test")
+    torch.manual_seed(1); b = pk(X, mode="test")
+    assert _rel(b, a) < 1e-5
+
+
 def test_train_phase1_tracks_reference_log(cpu_backend, traj):
     """Host logic of train_phase1 (batch draw, noise-draw order, check block, best-model restore)
     against the reference's golden log, first 101 iterations; generator state ends where the

@@ -117,7 +117,7 @@ def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0, lookback=5
     X_all = torch.cat([arrange_input(x, context)[0] for x in X], dim=0)
     run = CSPhase1Runner(crvae, lr, lam, lam_ridge, lambda_cs)
     # evaluation engine on ALL windows (:606) sharing the parameter arena
-    ev = CRVAEEngine(eng.p, eng.mask_np, head_off=eng.head_off, device=eng.device, group=eng.group)
+    ev = CRVAEEngine(eng.p, eng.mask_np, head_off=eng.head_off, device=eng.device, group=eng.group, packed=eng.packed)
     ev.theta = eng.theta
     if hasattr(eng, "w_ih_hi"):
         pass

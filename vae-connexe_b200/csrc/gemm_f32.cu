@@ -299,3 +299,67 @@ extern "C" int crvae_proj_wgrad(const float* dgates, const float* x, const uint8
                     x + (long long)t_skip * B * K, K, 0, dw_ih, K, (long long)G * K, nullptr, 0, mask, K,
                     0, splits, (float*)workspace, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Gather-packed ragged heads (phase 2, CRVAE_lorenz96.py:115, :200-201, :788-790): head i reads only its k_i connected
+// series, so its first-layer weight is (3H, k_i), not (3H, p).  Packed storage: w_ih [P, G, Kp] with Kp = the widest
+// head's input count rounded up to 4, cols [P, Kp] the series index of every packed column (ascending; padding columns
+// are masked), xg [P, T, B, Kp] the per-head gathered input.  The two GEMMs are the exact FFMA kernel with a per-head A /
+// B operand; summing the packed columns in ascending series order is the masked-dense sum with its exact zeros removed,
+// so the two forms agree BIT FOR BIT (the reduction of the weight gradient is cut into the same number of splits the
+// masked-dense form would use for `K_dense` series).
+// ------------------------------------------------------------------------------------------------------------------
+namespace crvae {
+__global__ void gather_cols_kernel(const float* __restrict__ x, const int* __restrict__ cols, const uint8_t* __restrict__ mask,
+                                   float* __restrict__ xg, int P, long long rows, int K, int Kp) {
+    const long long n = (long long)P * rows * Kp;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % Kp);
+        const long long r = (e / Kp) % rows;
+        const int i = (int)(e / ((long long)Kp * rows));
+        const bool live = mask == nullptr || mask[(long long)i * Kp + c] != 0;
+        xg[e] = live ? __ldg(x + r * K + cols[(long long)i * Kp + c]) : 0.f;
+    }
+}
+}  // namespace crvae
+
+extern "C" int crvae_gather_cols(const float* x, const int* cols, const uint8_t* mask, float* xg, int P, int64_t rows, int K,
+                                 int Kp, void* stream) {
+    CRVAE_REQUIRE(x && cols && xg && P >= 0 && rows >= 0 && K > 0 && Kp > 0, "bad argument");
+    const long long n = (long long)P * rows * Kp;
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gather_cols_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, cols, mask, xg, P, rows, K, Kp);
+    return check_launch("gather_cols_kernel");
+}
+
+extern "C" int crvae_proj_fwd_packed(const float* xg, const float* w_ih, const float* b_ih, float* gates,
+                                     int P, int T, int B, int Kp, int t_skip, void* stream) {
+    CRVAE_REQUIRE(xg && w_ih && b_ih && gates, "null operand");
+    CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0 && Kp > 0 && t_skip >= 0 && t_skip <= T, "bad size");
+    const int G = CRVAE_G;
+    const int M = (T - t_skip) * B;
+    return gemm_f32(CRVAE_GEMM_NT, P, M, G, Kp, xg + (long long)t_skip * B * Kp, Kp, (long long)T * B * Kp, w_ih, Kp,
+                    (long long)G * Kp, gates + (long long)t_skip * B * G, G, (long long)T * B * G, b_ih, G,
+                    nullptr, 0, 0, 1, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" size_t crvae_proj_wgrad_packed_workspace(int P, int T, int B, int Kp, int K_dense) {
+    int splits = pick_splits(P, CRVAE_G, K_dense, T * B);
+    return splits > 1 ? (size_t)P * splits * CRVAE_G * Kp * sizeof(float) : 16;
+}
+
+extern "C" int crvae_proj_wgrad_packed(const float* dgates, const float* xg, const uint8_t* mask, float* dw_ih,
+                                       int P, int T, int B, int Kp, int K_dense, int t_skip, void* workspace, void* stream) {
+    CRVAE_REQUIRE(dgates && xg && dw_ih, "null operand");
+    CRVAE_REQUIRE(P >= 0 && T > 0 && B > 0 && Kp > 0 && K_dense >= Kp / 4 && t_skip >= 0 && t_skip <= T, "bad size");
+    const int G = CRVAE_G;
+    const int R = (T - t_skip) * B;
+    const int splits = pick_splits(P, G, K_dense, T * B);
+    if (splits > 1) CRVAE_REQUIRE(workspace, "workspace required");
+    if (R == 0) return (int)cudaMemsetAsync(dw_ih, 0, (size_t)P * G * Kp * sizeof(float), (cudaStream_t)stream);
+    return gemm_f32(CRVAE_GEMM_TN, P, G, Kp, R, dgates + (long long)t_skip * B * G, G, (long long)T * B * G,
+                    xg + (long long)t_skip * B * Kp, Kp, (long long)T * B * Kp, dw_ih, Kp, (long long)G * Kp, nullptr, 0, mask, Kp,
+                    0, splits, (float*)workspace, (cudaStream_t)stream);
+}

@@ -65,7 +65,7 @@ class CRVAEEngine:
     """Kernel-level implementation of CRVAE.forward(mode='train') (:203-221), the trainer's loss
     (:484-489), backward (:497), GD (:498-499) and prox (:502-504) for a head shard."""
 
-    def __init__(self, p: int, mask: np.ndarray, head_off: int = 0, device="cuda", group=None, comm=None):
+    def __init__(self, p: int, mask: np.ndarray, head_off: int = 0, device="cuda", group=None, comm=None, packed=None):
         self.k = L.kernels()
         self.p = int(p)
         self.P = int(mask.shape[0])
@@ -81,23 +81,53 @@ class CRVAEEngine:
         assert mask.shape == (self.P, self.p)
         self.mask_np = np.ascontiguousarray(mask.astype(bool))
         self.dense = bool(self.mask_np.all())
-        self.mask_u8 = None if self.dense else torch.from_numpy(self.mask_np.astype(np.uint8)).to(self.device)
         P, p_ = self.P, self.p
+        # Pruned (phase-2) heads, two storage forms (:115, :200-201, :788-790):
+        #   masked-dense  w_ih [P,G,p] with structural zeros and a [P,p] mask (any graph; keeps the tensor-core projection)
+        #   gather-packed w_ih [P,G,Kp], Kp = widest head's input count rounded up to 4, with the per-head column lists
+        #                 `cols` and the gathered input dec_in_g [P,Td,B,Kp]: weights, gradients, projection flops and
+        #                 prox traffic scale with the graph's in-degree, not with p.  Chosen by default when every head
+        #                 reads at most a quarter of the series; bit-identical to the exact masked-dense form.
+        kmax = int(self.mask_np.sum(1).max()) if P > 0 else 0
+        if packed is None:
+            import os as _os0
+            packed = (not self.dense) and P > 0 and 4 * kmax <= p_ and _os0.environ.get("CRVAE_PACKED", "1") != "0"
+        self.packed = bool(packed) and hasattr(self.k, "proj_fwd_packed") and not self.dense and P > 0
+        if self.packed:
+            self.Kw = Kp = max(4, (kmax + 3) // 4 * 4)
+            cols = np.zeros((P, Kp), dtype=np.int32)
+            pmask = np.zeros((P, Kp), dtype=np.uint8)
+            for i in range(P):
+                c = np.where(self.mask_np[i])[0]                     # ascending = the reference's np.where order (:115)
+                cols[i, :len(c)] = c
+                pmask[i, :len(c)] = 1
+            self.cols_np, self.pmask_np = cols, pmask.astype(bool)
+            self.cols = torch.from_numpy(cols).to(self.device)
+            self.mask_u8 = torch.from_numpy(pmask).to(self.device)
+        else:
+            self.Kw = p_
+            self.mask_u8 = None if self.dense else torch.from_numpy(self.mask_np.astype(np.uint8)).to(self.device)
         shapes = {
-            "w_ih": (P, G, p_), "w_hh": (P, G, H), "b_ih": (P, G), "b_hh": (P, G), "w_lin": (P, H), "b_lin": (P,),
+            "w_ih": (P, G, self.Kw), "w_hh": (P, G, H), "b_ih": (P, G), "b_hh": (P, G), "w_lin": (P, H), "b_lin": (P,),
             "enc_w_ih": (G, p_), "enc_w_hh": (G, H), "enc_b_ih": (G,), "enc_b_hh": (G,),
             "lat_w": (2 * H, H), "lat_b": (2 * H,),
         }
         self.theta = Arena(shapes, self.device)
         self.grad = self.theta.like()
-        self.n_wih = P * G * p_
+        self.n_wih = P * G * self.Kw
         self.rest_off = self.theta.offsets["w_hh"]
-        self.col_norm = torch.zeros(P, p_, dtype=torch.float32, device=self.device)
-        # projection mode: "tc3" = tcgen05 3xTF32 (needs p % 4 == 0 for the TMA row pitch), "exact" = FFMA fp32
-        self.proj_mode = "tc3" if (p_ % 4 == 0 and hasattr(self.k, "proj_wgrad_tc")) else "exact"
+        self.col_norm = torch.zeros(P, self.Kw, dtype=torch.float32, device=self.device)
+        self.col_norm_dense = torch.zeros(P, p_, dtype=torch.float32, device=self.device) if self.packed else self.col_norm
+        # projection mode: "tc3" = tcgen05 3xTF32 (needs p % 4 == 0 for the TMA row pitch), "exact" = FFMA fp32,
+        # "packed" = gather-packed ragged heads (exact FFMA on Kp columns); the encoder (always dense) has its own flag
+        import os as _os1
+        tc_ok = p_ % 4 == 0 and hasattr(self.k, "proj_wgrad_tc") and _os1.environ.get("CRVAE_PROJ_MODE", "tc3") == "tc3"
+        self.enc_tc = tc_ok
+        self.proj_mode = "packed" if self.packed else ("tc3" if tc_ok else "exact")
+        zl = lambda t: torch.zeros_like(t)
         if self.proj_mode == "tc3":
-            zl = lambda t: torch.zeros_like(t)
             self.w_ih_hi, self.w_ih_lo = zl(self.theta["w_ih"]), zl(self.theta["w_ih"])
+        if self.enc_tc:
             self.enc_w_hi, self.enc_w_lo = zl(self.theta["enc_w_ih"]), zl(self.theta["enc_w_ih"])
         # recurrence mode: "tc3" = tcgen05 gate GEMM (crvae_gru_fwd_tc, 3xTF32; default once a rank holds enough heads
         # to fill the SMs with 128-row tiles), "exact" = persistent fp32 FFMA kernel (CRVAE_REC_MODE=exact, small shards)
@@ -134,22 +164,28 @@ class CRVAEEngine:
             self.dec_in = torch.zeros(DEC_STEPS, B, self.p, dtype=torch.float32, device=self.device)
             self.target = torch.empty(max(self.P, 1), DEC_STEPS, B, dtype=torch.float32, device=self.device)
         # in-place (re)binding keeps the buffer addresses stable for captured CUDA graphs
-        tc = self.proj_mode == "tc3"
-        if tc and (getattr(self, "enc_in_hi", None) is None or self.enc_in_hi.shape != self.enc_in.shape):
+        etc, dtc = self.enc_tc, self.proj_mode == "tc3"
+        if etc and (getattr(self, "enc_in_hi", None) is None or self.enc_in_hi.shape != self.enc_in.shape):
             self.enc_in_hi, self.enc_in_lo = torch.zeros_like(self.enc_in), torch.zeros_like(self.enc_in)
+        if dtc and (getattr(self, "dec_in_hi", None) is None or self.dec_in_hi.shape != self.dec_in.shape):
             self.dec_in_hi, self.dec_in_lo = torch.zeros_like(self.dec_in), torch.zeros_like(self.dec_in)
+        if self.packed and (getattr(self, "dec_in_g", None) is None or self.dec_in_g.shape[2] != B):
+            self.dec_in_g = torch.zeros(self.P, DEC_STEPS, B, self.Kw, dtype=torch.float32, device=self.device)
         if hasattr(self.k, "bind_batch") and X.is_contiguous():      # one pass: transposes + tf32 splits + targets
-            self.k.bind_batch(X, self.enc_in, self.enc_in_hi if tc else None, self.enc_in_lo if tc else None, self.dec_in,
-                              self.dec_in_hi if tc else None, self.dec_in_lo if tc else None, self.target, B, self.p,
+            self.k.bind_batch(X, self.enc_in, self.enc_in_hi if etc else None, self.enc_in_lo if etc else None, self.dec_in,
+                              self.dec_in_hi if dtc else None, self.dec_in_lo if dtc else None, self.target, B, self.p,
                               ENC_STEPS, DEC_STEPS, lo, self.P)
-            return
-        self.enc_in.copy_(X[:, :ENC_STEPS].transpose(0, 1))                               # [Te,B,p]
-        self.dec_in[1:].copy_(X[:, ENC_STEPS:-1].transpose(0, 1))                         # [Td,B,p], step 0 stays 0
-        if self.P > 0:
-            self.target[: self.P].copy_(X[:, ENC_STEPS:, lo:hi].permute(2, 1, 0))         # [P,Td,B]
-        if tc:      # the batch is fixed (:470-473): split it into tf32 hi/lo once
-            self.k.split_tf32(self.enc_in, self.enc_in_hi, self.enc_in_lo, self.enc_in.numel())
-            self.k.split_tf32(self.dec_in, self.dec_in_hi, self.dec_in_lo, self.dec_in.numel())
+        else:
+            self.enc_in.copy_(X[:, :ENC_STEPS].transpose(0, 1))                               # [Te,B,p]
+            self.dec_in[1:].copy_(X[:, ENC_STEPS:-1].transpose(0, 1))                         # [Td,B,p], step 0 stays 0
+            if self.P > 0:
+                self.target[: self.P].copy_(X[:, ENC_STEPS:, lo:hi].permute(2, 1, 0))         # [P,Td,B]
+            if etc:     # the batch is fixed (:470-473): split it into tf32 hi/lo once
+                self.k.split_tf32(self.enc_in, self.enc_in_hi, self.enc_in_lo, self.enc_in.numel())
+            if dtc:
+                self.k.split_tf32(self.dec_in, self.dec_in_hi, self.dec_in_lo, self.dec_in.numel())
+        if self.packed:     # every head's own input columns (:115), gathered once per batch
+            self.k.gather_cols(self.dec_in, self.cols, self.mask_u8, self.dec_in_g, self.P, DEC_STEPS * B, self.p, self.Kw)
 
     def _alloc(self, B: int):
         P, dev = self.P, self.device
@@ -186,6 +222,8 @@ class CRVAEEngine:
         self.ws_gru_enc = torch.zeros(k.gru_bwd_workspace(1, B) // 4 + 4, dtype=torch.float32, device=dev)
         nbytes = max(k.proj_wgrad_workspace(max(P, 1), DEC_STEPS, B, self.p),
                      k.proj_wgrad_workspace(1, ENC_STEPS, B, self.p))
+        if self.packed:
+            nbytes = max(nbytes, k.proj_wgrad_packed_workspace(P, DEC_STEPS, B, self.Kw, self.p))
         self.ws_wgrad = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)
         self.ws_wgrad_dec = torch.zeros(nbytes // 4 + 4, dtype=torch.float32, device=dev)   # side-stream twin
         self.ws_lat = None
@@ -197,7 +235,8 @@ class CRVAEEngine:
         if hasattr(k, "proj_wgrad_tc_workspace"):
             self.ws_wgrad_tc_enc = torch.zeros(k.proj_wgrad_tc_workspace(1, ENC_STEPS, B, self.p, 0) // 4 + 4, dtype=torch.float32, device=dev)
         if hasattr(k, "proj_wgrad_tc_workspace") and P > 0:     # split-reduction partials of the tensor-core gradient GEMMs
-            self.ws_wgrad_tc = torch.zeros(k.proj_wgrad_tc_workspace(P, DEC_STEPS, B, self.p, 1) // 4 + 4, dtype=torch.float32, device=dev)
+            if self.proj_mode == "tc3":
+                self.ws_wgrad_tc = torch.zeros(k.proj_wgrad_tc_workspace(P, DEC_STEPS, B, self.p, 1) // 4 + 4, dtype=torch.float32, device=dev)
             self.ws_dwhh = torch.zeros(k.gru_dwhh_tc_workspace(P, DEC_STEPS, B) // 4 + 4, dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------ forward
@@ -268,7 +307,10 @@ class CRVAEEngine:
     def _project(self, x, which, w, b, gates, P, T, t_skip):
         """gates = b + x . w^T for all heads / timesteps: tcgen05 3xTF32 GEMM or exact FFMA GEMM."""
         k = self.k
-        if self.proj_mode == "tc3":
+        if which == "dec" and self.packed:
+            k.proj_fwd_packed(self.dec_in_g, w, b, gates, P, T, self.B, self.Kw, t_skip)
+            return
+        if (self.enc_tc if which == "enc" else self.proj_mode == "tc3"):
             x_hi, x_lo = (self.enc_in_hi, self.enc_in_lo) if which == "enc" else (self.dec_in_hi, self.dec_in_lo)
             w_hi, w_lo = (self.enc_w_hi, self.enc_w_lo) if which == "enc" else (self.w_ih_hi, self.w_ih_lo)
             k.split_tf32_gate_rows(w, w_hi, w_lo, P * G, self.p)      # weights change every iteration; rows permuted for the epilogue
@@ -339,7 +381,7 @@ class CRVAEEngine:
             R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
                                  None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
                                  1, ENC_STEPS, B, self.ws_gru_enc, self.ws_dwhh_enc)
-            if self.proj_mode == "tc3" and self.ws_wgrad_tc_enc is not None:     # tcgen05, reduction split over 16 CTAs
+            if self.enc_tc and self.ws_wgrad_tc_enc is not None:     # tcgen05, reduction split over 16 CTAs
                 k.proj_wgrad_tc(self.enc_gates, self.enc_in_hi, self.enc_in_lo, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0,
                                 self.ws_wgrad_tc_enc)
             else:
@@ -347,7 +389,9 @@ class CRVAEEngine:
         if P > 0:
             if defer:
                 k.gru_dwhh_tc(self.gates, self.ghn, self.hs, self.zlat, 0, g["w_hh"], P, DEC_STEPS, B, self.ws_dwhh)
-            if self.proj_mode == "tc3":
+            if self.packed:
+                k.proj_wgrad_packed(self.gates, self.dec_in_g, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, self.Kw, p_, 1, self.ws_wgrad_dec)
+            elif self.proj_mode == "tc3":
                 k.proj_wgrad_tc(self.gates, self.dec_in_hi, self.dec_in_lo, self.mask_u8, g["w_ih"], P, DEC_STEPS, B, p_, 1,
                                 self.ws_wgrad_tc)
             else:
@@ -373,21 +417,41 @@ class CRVAEEngine:
         """GD on every parameter (:498-499) + group-lasso prox on the heads' w_ih (:502-504)."""
         k = self.k
         if self.P > 0:
-            k.gd_prox_gc(self.theta["w_ih"], self.grad["w_ih"], self.mask_u8, self.col_norm, self.P, self.p,
+            k.gd_prox_gc(self.theta["w_ih"], self.grad["w_ih"], self.mask_u8, self.col_norm, self.P, self.Kw,
                          _f32(lr), _f32(lam * lr), lam > 0)
         n_rest = self.theta.numel - self.rest_off
         k.gd_step(self.theta.flat[self.rest_off:], self.grad.flat[self.rest_off:], n_rest, _f32(lr))
 
     def prox_only(self, lam: float, lr: float):
         if self.P > 0:
-            self.k.gd_prox_gc(self.theta["w_ih"], None, self.mask_u8, self.col_norm, self.P, self.p,
+            self.k.gd_prox_gc(self.theta["w_ih"], None, self.mask_u8, self.col_norm, self.P, self.Kw,
                               0.0, _f32(lam * lr), True)
 
     def column_norms(self) -> torch.Tensor:
         """||w_ih[i][:, j]||_2 for the current weights -- what GC() stacks (:297-299)."""
         if self.P > 0:
-            self.k.gd_prox_gc(self.theta["w_ih"], None, self.mask_u8, self.col_norm, self.P, self.p, 0.0, 0.0, False)
-        return self.col_norm
+            self.k.gd_prox_gc(self.theta["w_ih"], None, self.mask_u8, self.col_norm, self.P, self.Kw, 0.0, 0.0, False)
+        if self.packed:     # packed column c of head i is series cols[i][c]
+            self.col_norm_dense.zero_()
+            self.col_norm_dense.scatter_(1, self.cols.long(), self.col_norm * self.mask_u8.float())
+        return self.col_norm_dense
+
+    # ------------------------------------------------------------------ packed <-> dense views of w_ih-shaped tensors
+    def unpack_w(self, w: torch.Tensor) -> torch.Tensor:
+        """[P,G,Kw] storage -> masked-dense [P,G,p] (identity for a dense / masked-dense engine)."""
+        if not self.packed:
+            return w
+        out = torch.zeros(self.P, G, self.p, dtype=w.dtype, device=w.device)
+        idx = self.cols.long().to(w.device)[:, None, :].expand(-1, G, -1)
+        out.scatter_(2, idx, w * self.mask_u8.to(w.device).to(w.dtype)[:, None, :])
+        return out
+
+    def pack_w(self, dense: torch.Tensor) -> torch.Tensor:
+        """masked-dense [P,G,p] -> [P,G,Kw] storage."""
+        if not self.packed:
+            return dense
+        idx = self.cols.long().to(dense.device)[:, None, :].expand(-1, G, -1)
+        return dense.gather(2, idx) * self.mask_u8.to(dense.device).to(dense.dtype)[:, None, :]
 
     def ridge_value(self, lam_ridge: float) -> torch.Tensor:
         """sum_i ridge_regularize(net_i, lam) (:321-325, :488) for this shard, as a device scalar."""

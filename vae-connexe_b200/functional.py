@@ -26,7 +26,7 @@ def prox_update(network, lam, lr):
     W[:,j] <- W[:,j] / max(||W[:,j]||, lam*lr) * max(||W[:,j]|| - lr*lam, 0)."""
     eng, i = _head(network)
     mask = None if eng.mask_u8 is None else eng.mask_u8[i:i + 1]
-    eng.k.gd_prox_gc(eng.theta["w_ih"][i:i + 1], None, mask, eng.col_norm[i:i + 1], 1, eng.p,
+    eng.k.gd_prox_gc(eng.theta["w_ih"][i:i + 1], None, mask, eng.col_norm[i:i + 1], 1, eng.Kw,
                      0.0, _f32(lam * lr), True)
     network.gru.flatten_parameters()
 
@@ -35,7 +35,7 @@ def regularize(network, lam):
     """lam * sum_j ||W[:,j]||_2 over the head's input columns (:316-319)."""
     eng, i = _head(network)
     mask = None if eng.mask_u8 is None else eng.mask_u8[i:i + 1]
-    eng.k.gd_prox_gc(eng.theta["w_ih"][i:i + 1], None, mask, eng.col_norm[i:i + 1], 1, eng.p, 0.0, 0.0, False)
+    eng.k.gd_prox_gc(eng.theta["w_ih"][i:i + 1], None, mask, eng.col_norm[i:i + 1], 1, eng.Kw, 0.0, 0.0, False)
     return lam * torch.sum(eng.col_norm[i])
 
 

@@ -43,6 +43,7 @@ class _CrvaePlan:
         self.tc = eng.proj_mode == "tc3"
         self.x_hi, self.x_lo = (z(1, B, p), z(1, B, p)) if self.tc else (None, None)
         self.gates, self.ghn, self.pred = z(max(P, 1), 1, B, G), z(max(P, 1), 1, B, H), z(max(P, 1), 1, B)
+        self.xg = z(P, 1, B, eng.Kw) if eng.packed else None       # gather-packed heads: every head's own input columns
         self.out = z(B, GEN_STEPS, p)
         self.noise = z(B, GEN_STEPS, p) if phase == 1 else None
         self.world = model.world_size
@@ -58,7 +59,10 @@ class _CrvaePlan:
         eng, k, th, P, p, B = self.eng, self.k, self.eng.theta, self.eng.P, self.eng.p, self.B
         h, h_next = self.h[i & 1], self.h[(i + 1) & 1]
         if P > 0:
-            if self.tc:
+            if eng.packed:
+                k.gather_cols(self.x, eng.cols, eng.mask_u8, self.xg, P, B, p, eng.Kw)
+                k.proj_fwd_packed(self.xg, th["w_ih"], th["b_ih"], self.gates, P, 1, B, eng.Kw, 0)
+            elif self.tc:
                 k.proj_fwd_tc(self.x_hi, self.x_lo, eng.w_ih_hi, eng.w_ih_lo, th["b_ih"], self.gates, P, 1, B, p, 0)
             else:
                 k.proj_fwd(self.x, th["w_ih"], th["b_ih"], self.gates, P, 1, B, p, 0)

@@ -61,6 +61,10 @@ SIGNATURES = {
     "crvae_act_fwd": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_int, _c_void_p]),
     "crvae_act_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_int, _c_void_p]),
     "crvae_transpose": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "crvae_gather_cols": (_c_int, [_c_void_p] * 4 + [_c_int, _c_i64, _c_int, _c_int, _c_void_p]),
+    "crvae_proj_fwd_packed": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p]),
+    "crvae_proj_wgrad_packed_workspace": (_c_size_t, [_c_int] * 5),
+    "crvae_proj_wgrad_packed": (_c_int, [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p, _c_void_p]),
     "crvae_gen_scatter": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_float, _c_void_p]),
     "crvae_sumsq": (_c_int, [_c_void_p, _c_i64, _c_void_p, _c_void_p]),
     "crvae_dot_small": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p]),
@@ -285,6 +289,20 @@ class Kernels:
 
     def transpose(self, src, dst, rows, cols):
         self._ck(self.lib.crvae_transpose(ptr(src), ptr(dst), rows, cols, stream_ptr()), "crvae_transpose")
+
+    def gather_cols(self, x, cols, mask, xg, P, rows, K, Kp):
+        self._ck(self.lib.crvae_gather_cols(ptr(x), ptr(cols), ptr(mask), ptr(xg), P, rows, K, Kp, stream_ptr()), "crvae_gather_cols")
+
+    def proj_fwd_packed(self, xg, w_ih, b_ih, gates, P, T, B, Kp, t_skip):
+        self._ck(self.lib.crvae_proj_fwd_packed(ptr(xg), ptr(w_ih), ptr(b_ih), ptr(gates), P, T, B, Kp, t_skip, stream_ptr()),
+                 "crvae_proj_fwd_packed")
+
+    def proj_wgrad_packed_workspace(self, P, T, B, Kp, K_dense) -> int:
+        return int(self.lib.crvae_proj_wgrad_packed_workspace(P, T, B, Kp, K_dense))
+
+    def proj_wgrad_packed(self, dgates, xg, mask, dw_ih, P, T, B, Kp, K_dense, t_skip, ws):
+        self._ck(self.lib.crvae_proj_wgrad_packed(ptr(dgates), ptr(xg), ptr(mask), ptr(dw_ih), P, T, B, Kp, K_dense, t_skip, ptr(ws),
+                                                  stream_ptr()), "crvae_proj_wgrad_packed")
 
     def gen_scatter(self, y, noise, x, x_hi, x_lo, out, B, p, t, steps, base, rem, widest, scale):
         self._ck(self.lib.crvae_gen_scatter(ptr(y), ptr(noise), ptr(x), ptr(x_hi), ptr(x_lo), ptr(out), B, p, t, steps, base, rem,

@@ -51,8 +51,8 @@ class _LinearParams(nn.Module):
 
 class GRU(nn.Module):
     """One decoder head (reference class GRU, :97-121) as a *view* into the fused engine.
-    For a pruned head the reference stores a packed (3H, k_i) weight_ih_l0; here the view is the
-    masked-dense (3H, p) row block (structural zeros in unconnected columns)."""
+    For a pruned head the reference stores a packed (3H, k_i) weight_ih_l0: with the engine's gather-packed storage the
+    view IS that (3H, k_i) matrix; with masked-dense storage it is the (3H, p) row block with structural zeros."""
 
     def __init__(self, owner: "CRVAE", local_idx: int):
         super().__init__()
@@ -61,8 +61,9 @@ class GRU(nn.Module):
         i = local_idx
         self.p = int(eng.mask_np[i].sum())
         self.hidden = _H
-        self.gru = _GRUParams(th["w_ih"][i], th["w_hh"][i], th["b_ih"][i], th["b_hh"][i],
-                              g["w_ih"][i], g["w_hh"][i], g["b_ih"][i], g["b_hh"][i])
+        w_ih, gw_ih = (th["w_ih"][i][:, :self.p], g["w_ih"][i][:, :self.p]) if eng.packed else (th["w_ih"][i], g["w_ih"][i])
+        self.gru = _GRUParams(w_ih, th["w_hh"][i], th["b_ih"][i], th["b_hh"][i],
+                              gw_ih, g["w_hh"][i], g["b_ih"][i], g["b_hh"][i])
         self.linear = _LinearParams(th["w_lin"][i:i + 1], th["b_lin"][i:i + 1], g["w_lin"][i:i + 1], g["b_lin"][i:i + 1])
         self._owner = [owner]          # list: keep nn.Module from registering the parent as a child
         self._local_idx = i
@@ -128,7 +129,7 @@ class CRVAE(nn.Module):
     constructing the same torch modules, so torch.manual_seed(s) gives the reference's weights."""
 
     def __init__(self, num_series, connection, hidden, rank: int = 0, world_size: int = 1, group=None,
-                 device: Optional[str] = None, _init: bool = True, comm=None):
+                 device: Optional[str] = None, _init: bool = True, comm=None, packed=None):
         super().__init__()
         _require_hidden(hidden)
         kern = L.kernels()                 # raises without libcrvae_b200.so + a B200: there is no CPU path
@@ -147,8 +148,9 @@ class CRVAE(nn.Module):
         lo, hi = head_range(self.p, rank, world_size)
         self.head_lo, self.head_hi = lo, hi
         full_mask = (conn != 0).T                       # head i reads column j iff connection[j, i] != 0 (:115, :201)
+        # packed: None = automatic (gather-packed storage when every head reads <= p/4 series), True / False = forced
         self.engine = CRVAEEngine(self.p, full_mask[lo:hi], head_off=lo, device=self.device,
-                                  group=group if world_size > 1 else None, comm=comm if world_size > 1 else None)
+                                  group=group if world_size > 1 else None, comm=comm if world_size > 1 else None, packed=packed)
         if _init:
             self._init_like_reference(full_mask, lo, hi)
         eng = self.engine
@@ -179,7 +181,7 @@ class CRVAE(nn.Module):
             th["lat_w"][:_H].copy_(fc_mu.weight); th["lat_w"][_H:].copy_(fc_std.weight)
             th["lat_b"][:_H].copy_(fc_mu.bias); th["lat_b"][_H:].copy_(fc_std.bias)
             P = hi - lo
-            w_ih = torch.zeros(P, _G, self.p)
+            w_ih = torch.zeros(P, _G, eng.Kw)
             w_hh, b_ih, b_hh = torch.zeros(P, _G, _H), torch.zeros(P, _G), torch.zeros(P, _G)
             w_lin, b_lin = torch.zeros(P, _H), torch.zeros(P)
             for i in range(self.p):                                       # :200-201, every head draws in order
@@ -188,7 +190,10 @@ class CRVAE(nn.Module):
                 lin = nn.Linear(_H, 1)                                    # :106
                 if lo <= i < hi:
                     j = i - lo
-                    w_ih[j][:, cols] = gru.weight_ih_l0
+                    if eng.packed:
+                        w_ih[j][:, :len(cols)] = gru.weight_ih_l0
+                    else:
+                        w_ih[j][:, cols] = gru.weight_ih_l0
                     w_hh[j], b_ih[j], b_hh[j] = gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0
                     w_lin[j], b_lin[j] = lin.weight[0], lin.bias[0]
             for name, val in (("w_ih", w_ih), ("w_hh", w_hh), ("b_ih", b_ih), ("b_hh", b_hh), ("w_lin", w_lin),
@@ -218,7 +223,7 @@ class CRVAE(nn.Module):
         for j in range(eng.P):
             i = self.head_lo + j
             cols = torch.from_numpy(np.where(eng.mask_np[j])[0]).to(self.device)
-            sd[f"networks.{i}.gru.weight_ih_l0"] = th["w_ih"][j].index_select(1, cols)
+            sd[f"networks.{i}.gru.weight_ih_l0"] = th["w_ih"][j][:, :len(cols)] if eng.packed else th["w_ih"][j].index_select(1, cols)
             sd[f"networks.{i}.gru.weight_hh_l0"] = th["w_hh"][j]
             sd[f"networks.{i}.gru.bias_ih_l0"] = th["b_ih"][j]
             sd[f"networks.{i}.gru.bias_hh_l0"] = th["b_hh"][j]
@@ -237,7 +242,10 @@ class CRVAE(nn.Module):
             for j in range(eng.P):
                 i = self.head_lo + j
                 cols = torch.from_numpy(np.where(eng.mask_np[j])[0]).to(self.device)
-                th["w_ih"][j].index_copy_(1, cols, sd[f"networks.{i}.gru.weight_ih_l0"].to(self.device))
+                if eng.packed:
+                    th["w_ih"][j][:, :len(cols)].copy_(sd[f"networks.{i}.gru.weight_ih_l0"])
+                else:
+                    th["w_ih"][j].index_copy_(1, cols, sd[f"networks.{i}.gru.weight_ih_l0"].to(self.device))
                 th["w_hh"][j].copy_(sd[f"networks.{i}.gru.weight_hh_l0"])
                 th["b_ih"][j].copy_(sd[f"networks.{i}.gru.bias_ih_l0"])
                 th["b_hh"][j].copy_(sd[f"networks.{i}.gru.bias_hh_l0"])
@@ -262,7 +270,7 @@ class CRVAE(nn.Module):
         """deepcopy(crvae) is how the reference snapshots its best model (:547): a device-side copy
         of the fused parameter arena into a fresh engine."""
         new = type(self)(*self._clone_args(), rank=self.rank, world_size=self.world_size, group=self.group,
-                         device=str(self.device), _init=False, comm=self.engine.comm)   # no init draws: the caller's generator is untouched
+                         device=str(self.device), _init=False, comm=self.engine.comm, packed=self.engine.packed)   # no init draws: the caller's generator is untouched
         new.engine.theta.flat.copy_(self.engine.theta.flat)
         new.engine.grad.flat.copy_(self.engine.grad.flat)
         self._copy_extra_to(new)
