@@ -296,11 +296,11 @@ def time_gpu_eager(Xb, p, dev, steps=5, warmup=2):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-def time_phase2(V, Xb_dev, p, B, steps):
+def time_phase2(V, Xb_dev, p, B, steps, packed=None):
     """Phase-2 iteration (CRVAE on the pruned Lorenz-96 graph + VRAE4E + Adam, CRVAE_lorenz96.py:609-643), graph replay."""
     from vae_connexe_b200.data import lorenz_96_graph
     torch.manual_seed(0)
-    c, v = V.CRVAE(p, lorenz_96_graph(p), 64), V.VRAE4E(p, 64)
+    c, v = V.CRVAE(p, lorenz_96_graph(p), 64, packed=packed), V.VRAE4E(p, 64)
     run = V.Phase2Runner(c, v, Xb_dev, LR, 0.0, 0.0)
     gen = torch.Generator().manual_seed(1)
     eps = [(torch.randn(B, H, generator=gen).cuda(), torch.randn(B, H, generator=gen).cuda()) for _ in range(8)]
@@ -316,7 +316,8 @@ def time_phase2(V, Xb_dev, p, B, steps):
     ms = s.elapsed_time(e) / steps
     out = {"ms_per_step": ms, "value": B * TD * p / (ms * 1e-3), "unit": UNIT, "steps": steps,
            "what": "train_phase2 iteration (:609-643): VRAE4E backward + Adam, CRVAE backward + GD, forward, residual, VRAE4E forward; "
-                   "connection = Lorenz-96 stencil (4 inputs per head, masked-dense)", "loss": float(c.engine.loss), "loss_e": float(v.engine.loss)}
+                   "connection = Lorenz-96 stencil (4 inputs per head, %s)" % ("gather-packed" if c.engine.packed else "masked-dense"),
+           "w_ih_bytes": int(c.engine.theta["w_ih"].numel() * 4), "loss": float(c.engine.loss), "loss_e": float(v.engine.loss)}
     run.g_full = run.g_update = run.g_fwd = None
     return out
 
@@ -326,6 +327,7 @@ def time_check_block(V, m, run, eps_dev, check_every=50, reps=5):
     21-step test-mode generation, amortised over check_every iterations."""
     eng = m.engine
     Xd = torch.zeros(eng.B, 20, eng.p, device=eng.device)
+    m(Xd, mode="test")                                     # first call captures the generator's CUDA graph
     torch.cuda.synchronize()
     t_gen = []
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

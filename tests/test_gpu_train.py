@@ -653,7 +653,7 @@ def test_phase2_iteration_p100_matches_oracle():
     p, B = 100, 256
     conn = lorenz_96_graph(p)
     torch.manual_seed(3)
-    cg, vr = V.CRVAE(p, conn, 64), V.VRAE4E(p, 64)
+    cg, vr = V.CRVAE(p, conn, 64, packed=False), V.VRAE4E(p, 64)      # masked-dense: the tensor-core projection with structural zeros
     prm = O.params_from_state_dict({k: v.cpu() for k, v in cg.state_dict().items()}, conn)
     vprm = O.vrae_params_from_state_dict({k: v.detach().cpu() for k, v in vr.state_dict().items()})
     gen = torch.Generator().manual_seed(8)
@@ -816,8 +816,8 @@ def test_gather_packed_heads_bitwise_equal_masked_dense_and_oracle():
     assert torch.equal(pk.GC(), md.GC())
     # (ii) oracle, one iteration from a fresh seed
     torch.manual_seed(4)
-    m = V.CRVAE(p, conn, 64)                                     # automatic: k = 4 <= p / 4 -> packed
-    assert m.engine.packed
+    m = V.CRVAE(p, conn, 64, packed=True)
+    assert m.engine.packed and not V.CRVAE(p, conn, 64).engine.packed      # automatic choice: packed only from p = 256 up
     prm = O.params_from_state_dict({k: v.cpu() for k, v in m.state_dict().items()}, conn)
     e = m.engine
     e.bind_batch(X.cuda()); e.forward(eps[0].cuda()); e.backward(1.0, 0.0)

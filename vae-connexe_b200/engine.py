@@ -86,12 +86,16 @@ class CRVAEEngine:
         #   masked-dense  w_ih [P,G,p] with structural zeros and a [P,p] mask (any graph; keeps the tensor-core projection)
         #   gather-packed w_ih [P,G,Kp], Kp = widest head's input count rounded up to 4, with the per-head column lists
         #                 `cols` and the gathered input dec_in_g [P,Td,B,Kp]: weights, gradients, projection flops and
-        #                 prox traffic scale with the graph's in-degree, not with p.  Chosen by default when every head
-        #                 reads at most a quarter of the series; bit-identical to the exact masked-dense form.
+        #                 prox traffic scale with the graph's in-degree, not with p.  Bit-identical to the exact
+        #                 masked-dense form.  Chosen by default when every head reads at most a quarter of the series AND
+        #                 p >= 256: measured phase-2 iteration, Lorenz-96 ring (k = 4), B = 256 -- p = 1000: 13.5 ms
+        #                 masked-dense (768 MB of W_ih) vs 7.4 ms packed (3 MB); p = 100: 1.10 vs 1.23 ms (at K = 100 the
+        #                 tensor-core projection on structural zeros still beats the exact FFMA GEMM on K = 4).
         kmax = int(self.mask_np.sum(1).max()) if P > 0 else 0
         if packed is None:
             import os as _os0
-            packed = (not self.dense) and P > 0 and 4 * kmax <= p_ and _os0.environ.get("CRVAE_PACKED", "1") != "0"
+            packed = ((not self.dense) and P > 0 and 4 * kmax <= p_ and p_ >= 256
+                      and _os0.environ.get("CRVAE_PACKED", "1") != "0")
         self.packed = bool(packed) and hasattr(self.k, "proj_fwd_packed") and not self.dense and P > 0
         if self.packed:
             self.Kw = Kp = max(4, (kmax + 3) // 4 * 4)
