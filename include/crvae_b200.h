@@ -47,6 +47,8 @@ extern "C" {
                                (pred, log_var, mu) (CRVAE_lorenz96.py:221) but the trainer unpacks
                                (pred, mu, log_var) (:482,:508), so the roles are exchanged:
                                -0.5*sum(1 + mu - log_var^2 - exp(mu))                             */
+#define CRVAE_KL_LOGSIGMA 2 /* Family-B CR-VAE (CRVAE.py:72-75, :169): the second half of `lat` is log(sigma), not log(var):
+                              z = mu + 0.5*exp(s)*eps,  KL term = -0.5*(1 + 2s - mu^2 - exp(2s))                   */
 
 int         crvae_abi_version(void);
 const char* crvae_last_error(void);
@@ -275,6 +277,14 @@ int crvae_proj_fwd_packed(const float* xg, const float* w_ih, const float* b_ih,
 size_t crvae_proj_wgrad_packed_workspace(int P, int T, int B, int Kp, int K_dense);
 int crvae_proj_wgrad_packed(const float* dgates, const float* xg, const uint8_t* mask, float* dw_ih,
                             int P, int T, int B, int Kp, int K_dense, int t_skip, void* workspace, void* stream);
+
+/* Family-B CR-VAE (CRVAE.py:134-150): ISTA step on the per-head input maps W_in[i] (D x H), one group per ROW
+ * (= one candidate parent series):  W_tmp = W - lr*dW;  W <- W_tmp * max(1 - thr/||W_tmp[row,:]||_2, 0)  with thr = lr*lambda
+ * (a zero row stays zero, as in the reference: 1 - thr/0 = -inf -> 0).  w / dw [rows, cols] row-major; row_norm [rows]
+ * receives ||W[row,:]||_2 of the RESULT (what granger_matrix thresholds, :126-131).  dw = NULL: no gradient step;
+ * do_prox = 0: norms only.                                                                                          */
+int crvae_ista_rows(float* w, const float* dw, float* row_norm, int64_t rows, int cols, float lr, float thr, int do_prox,
+                    void* stream);
 
 /* Test-mode generation (CRVAE.forward(mode='test'), CRVAE_lorenz96.py:223-243 / :264-284), the step between two
  * recurrent updates: every head's next input is the vector of ALL heads' outputs (:232-236).  y [R][W][B] = the step's

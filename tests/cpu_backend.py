@@ -32,22 +32,23 @@ class OracleKernels:
 
     # -- GEMM ------------------------------------------------------------------------------------
     def gemm(self, form, batch, M, N, K, A, lda, sA, Bm, ldb, sB, Cm, ldc, sC, bias=None, sBias=0, accumulate=False):
-        assert batch == 1, "checker backend: batch-1 generic GEMM only"
-        a, b = A.reshape(-1), Bm.reshape(-1)
-        if form == 0:      # NT
-            Am = torch.as_strided(a, (M, K), (lda, 1)); Bt = torch.as_strided(b, (N, K), (ldb, 1)).t()
-        elif form == 1:    # TN
-            Am = torch.as_strided(a, (K, M), (lda, 1)).t(); Bt = torch.as_strided(b, (K, N), (ldb, 1))
-        else:              # NN
-            Am = torch.as_strided(a, (M, K), (lda, 1)); Bt = torch.as_strided(b, (K, N), (ldb, 1))
-        out = Am @ Bt
-        if bias is not None:
-            out = out + bias.reshape(-1)[:N]
-        Cv = torch.as_strided(Cm.reshape(-1), (M, N), (ldc, 1))
-        if accumulate:
-            Cv += out
-        else:
-            Cv.copy_(out)
+        a, b, c = A.reshape(-1), Bm.reshape(-1), Cm.reshape(-1)
+        for i in range(batch):
+            ao, bo, co = a.storage_offset() + i * sA, b.storage_offset() + i * sB, c.storage_offset() + i * sC
+            if form == 0:      # NT
+                Am = torch.as_strided(a, (M, K), (lda, 1), ao); Bt = torch.as_strided(b, (N, K), (ldb, 1), bo).t()
+            elif form == 1:    # TN
+                Am = torch.as_strided(a, (K, M), (lda, 1), ao).t(); Bt = torch.as_strided(b, (K, N), (ldb, 1), bo)
+            else:              # NN
+                Am = torch.as_strided(a, (M, K), (lda, 1), ao); Bt = torch.as_strided(b, (K, N), (ldb, 1), bo)
+            out = Am @ Bt
+            if bias is not None:
+                out = out + bias.reshape(-1)[i * sBias:i * sBias + N]
+            Cv = torch.as_strided(c, (M, N), (ldc, 1), co)
+            if accumulate:
+                Cv += out
+            else:
+                Cv.copy_(out)
         self.launches += 1
 
     # -- projection ------------------------------------------------------------------------------
@@ -148,6 +149,11 @@ class OracleKernels:
     def latent_fwd(self, lat, eps, z, kl_out, B, kl_form, Z=64):
         H = Z
         mu, lv = lat[:, :H], lat[:, H:]
+        if kl_form == 2:                   # Family-B: lv holds log sigma (CRVAE.py:72-75, :169)
+            z.copy_(mu + torch.exp(lv) * 0.5 * eps.reshape(B, H))
+            kl_out[0] = (-0.5 * (1 + 2 * lv - mu * mu - torch.exp(2 * lv))).sum(-1).mean(0)
+            self.launches += 1
+            return
         z.copy_(mu + torch.exp(0.5 * lv) * eps.reshape(B, H))
         kl_out[0] = (-0.5 * self._kl_terms(mu, lv, kl_form)).sum(-1).mean(0)
         self.launches += 1
@@ -165,6 +171,10 @@ class OracleKernels:
         if dz_extra is not None:
             dz = dz + dz_extra
         mu, lv = lat[:, :H], lat[:, H:]
+        if kl_form == 2:
+            dlat[:, :H] = dz + beta * mu / B
+            dlat[:, H:] = dz * eps.reshape(B, H) * 0.5 * torch.exp(lv) + beta * (-(1 - torch.exp(2 * lv)) / B)
+            return
         if kl_form == 1:
             dkm, dkl = -0.5 * (1 - torch.exp(mu)) / B, lv / B
         else:
@@ -240,6 +250,18 @@ class OracleKernels:
 
     def transpose(self, src, dst, rows, cols):
         dst.reshape(-1)[: rows * cols].view(cols, rows).copy_(src.reshape(-1)[: rows * cols].view(rows, cols).t())
+        self.launches += 1
+
+    def ista_rows(self, w, dw, row_norm, rows, cols, lr, thr, do_prox):
+        wv = w.reshape(-1)[: rows * cols].view(rows, cols)
+        tmp = wv if dw is None else wv - torch.tensor(lr, dtype=torch.float32) * dw.reshape(-1)[: rows * cols].view(rows, cols)
+        nu = torch.norm(tmp, dim=1, keepdim=True)
+        shrink = torch.clamp(1 - torch.tensor(thr, dtype=torch.float32) / nu, min=0.) if do_prox else torch.ones_like(nu)
+        shrink = torch.nan_to_num(shrink, nan=0.0)
+        if do_prox or dw is not None:
+            wv.copy_(tmp * shrink)
+        if row_norm is not None:
+            row_norm.reshape(-1)[:rows] = (nu * shrink).reshape(-1)
         self.launches += 1
 
     def gen_scatter(self, y, noise, x, x_hi, x_lo, out, B, p, t, steps, base, rem, widest, scale):

@@ -854,3 +854,11 @@ def test_gather_packed_heads_bitwise_equal_masked_dense_and_oracle():
     eb.bind_batch(Xb.cuda()); eb.forward(torch.randn(256, H, generator=gen).cuda()); eb.backward(1.0, 0.0); eb.step(5e-2, 0.0)
     assert np.isfinite(float(eb.loss)) and bool(torch.isfinite(eb.theta.flat).all())
     assert eb.dec_in_g.numel() * 4 < 0.05 * (10 * 256 * p3 * p3 * 4)          # gathered inputs: Kp columns per head, not p
+
+
+def test_family_b_crvae_matches_reference():
+    """Family-B CR-VAE (reference CRVAE.py:55-199: W_in pre-projection + GRU(H->H) heads, row-group ISTA, Adam on
+    the rest, ErrorVAE stage 2) on the CUDA kernels against the fixture produced by the reference itself."""
+    from tests.family_b_check import run
+    m = run("cuda")
+    assert m.theta.flat.is_cuda

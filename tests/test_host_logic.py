@@ -201,6 +201,12 @@ def test_gather_packed_heads_equal_masked_dense(cpu_backend):
     assert _rel(b, a) < 1e-5
 
 
+def test_family_b_crvae_matches_reference(cpu_backend):
+    """the Family-B CR-VAE (CRVAE.py) host logic on the checker backend against the reference's own numbers."""
+    from tests.family_b_check import run
+    run("cpu", tol=2e-5)
+
+
 def test_train_phase1_tracks_reference_log(cpu_backend, traj):
     """Host logic of train_phase1 (batch draw, noise-draw order, check block, best-model restore)
     against the reference's golden log, first 101 iterations; generator state ends where the

@@ -9,7 +9,7 @@ shim module vae_connexe_b200.py at the repository root).
 from .functional import arrange_input, prox_update, regularize, restore_parameters, ridge_regularize
 from .modules import CRVAE, GRU, VRAE4E
 from .sharding import allgather_rows, head_range
-from . import driver
+from . import driver, family_b
 from .train import Phase1Runner, Phase2Runner, train_phase1, train_phase2
 
 __all__ = ["CRVAE", "GRU", "VRAE4E", "train_phase1", "train_phase2", "Phase1Runner", "Phase2Runner", "prox_update", "regularize", "ridge_regularize",

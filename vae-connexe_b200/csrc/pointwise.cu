@@ -33,11 +33,16 @@ __global__ void __launch_bounds__(1024) latent_fwd_kernel(const float* __restric
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         int b = e / Z, h = e % Z;
         float mu = lat[b * 2 * Z + h], lv = lat[b * 2 * Z + Z + h];
-        float sigma = expf(__fmul_rn(0.5f, lv));
-        z[e] = __fadd_rn(mu, __fmul_rn(sigma, eps[e]));
         float term;
-        if (kl_form == CRVAE_KL_SWAPPED) term = 1.f + mu - lv * lv - expf(mu);
-        else term = 1.f + lv - mu * mu - expf(lv);
+        if (kl_form == CRVAE_KL_LOGSIGMA) {          // lv holds log(sigma): z = mu + exp(s)*0.5*eps (CRVAE.py:74)
+            z[e] = __fadd_rn(mu, __fmul_rn(__fmul_rn(expf(lv), 0.5f), eps[e]));
+            term = 1.f + 2.f * lv - mu * mu - expf(2.f * lv);
+        } else {
+            float sigma = expf(__fmul_rn(0.5f, lv));
+            z[e] = __fadd_rn(mu, __fmul_rn(sigma, eps[e]));
+            if (kl_form == CRVAE_KL_SWAPPED) term = 1.f + mu - lv * lv - expf(mu);
+            else term = 1.f + lv - mu * mu - expf(lv);
+        }
         part += (double)(-0.5f * term);
     }
     double tot = block_sum(part, sh);
@@ -73,6 +78,13 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dh0, int P, const fl
     const float mu = lat[b * 2 * Z + h], lv = lat[b * 2 * Z + Z + h];
     const float invB = 1.f / (float)B;
     float dkl_mu, dkl_lv;
+    if (kl_form == CRVAE_KL_LOGSIGMA) {
+        dkl_mu = mu * invB;
+        dkl_lv = -(1.f - expf(2.f * lv)) * invB;
+        dlat[b * 2 * Z + h] = dz + beta * dkl_mu;
+        dlat[b * 2 * Z + Z + h] = dz * eps[e] * 0.5f * expf(lv) + beta * dkl_lv;
+        return;
+    }
     if (kl_form == CRVAE_KL_SWAPPED) {
         dkl_mu = -0.5f * (1.f - expf(mu)) * invB;
         dkl_lv = lv * invB;
@@ -437,6 +449,31 @@ extern "C" int crvae_tanh_bwd(const float* dy, const float* y, float* dx, int64_
 }
 
 namespace crvae {
+// Family-B ISTA (CRVAE.py:134-150): one warp per row of W_in (one candidate parent), norm over the row's H entries.
+__global__ void ista_rows_kernel(float* __restrict__ w, const float* __restrict__ dw, float* __restrict__ row_norm, long long rows,
+                                 int cols, float lr, float thr, int do_prox) {
+    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* wr = w + row * cols;
+    float ss = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+        float v = wr[c];
+        if (dw) v = __fsub_rn(v, __fmul_rn(lr, dw[row * cols + c]));       // W_tmp = W - lr * grad
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float nu = sqrtf(ss);
+    float shrink = 1.f;
+    if (do_prox) shrink = fmaxf(__fsub_rn(1.f, __fdiv_rn(thr, nu)), 0.f);  // thr / 0 = inf -> shrink = 0
+    if (do_prox || dw)
+        for (int c = lane; c < cols; c += 32) {
+            float v = wr[c];
+            if (dw) v = __fsub_rn(v, __fmul_rn(lr, dw[row * cols + c]));
+            wr[c] = do_prox ? __fmul_rn(v, shrink) : v;
+        }
+    if (lane == 0 && row_norm) row_norm[row] = nu * shrink;               // norm of the stored row
+}
 // Test-mode generation, the step between two recurrent updates (CRVAE_lorenz96.py:232-236, :281-283): the p heads' scalar
 // outputs of this step become the next input row of EVERY head.  y [R][W][B]: outputs gathered over R head shards of at
 // most W heads each (balanced contiguous partition: the first `rem` shards hold base+1 heads, the rest base); one pass
@@ -465,6 +502,15 @@ __global__ void gen_scatter_kernel(const float* __restrict__ y, const float* __r
 }
 
 }  // namespace crvae
+
+extern "C" int crvae_ista_rows(float* w, const float* dw, float* row_norm, int64_t rows, int cols, float lr, float thr, int do_prox,
+                               void* stream) {
+    CRVAE_REQUIRE(w && rows >= 0 && cols > 0 && lr >= 0.f && thr >= 0.f, "bad argument");
+    if (rows == 0) return 0;
+    const long long threads = rows * 32;
+    ista_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, dw, row_norm, rows, cols, lr, thr, do_prox);
+    return check_launch("ista_rows_kernel");
+}
 
 extern "C" int crvae_gen_scatter(const float* y, const float* noise, float* x, float* x_hi, float* x_lo, float* out, int B, int p,
                                  int t, int steps, int base, int rem, int widest, float scale, void* stream) {

@@ -65,6 +65,7 @@ SIGNATURES = {
     "crvae_proj_fwd_packed": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p]),
     "crvae_proj_wgrad_packed_workspace": (_c_size_t, [_c_int] * 5),
     "crvae_proj_wgrad_packed": (_c_int, [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p, _c_void_p]),
+    "crvae_ista_rows": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_int, _c_float, _c_float, _c_int, _c_void_p]),
     "crvae_gen_scatter": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_float, _c_void_p]),
     "crvae_sumsq": (_c_int, [_c_void_p, _c_i64, _c_void_p, _c_void_p]),
     "crvae_dot_small": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p]),
@@ -73,7 +74,7 @@ SIGNATURES = {
 }
 
 GEMM_NT, GEMM_TN, GEMM_NN = 0, 1, 2
-KL_STANDARD, KL_SWAPPED = 0, 1
+KL_STANDARD, KL_SWAPPED, KL_LOGSIGMA = 0, 1, 2
 
 _lib: Optional[C.CDLL] = None
 
@@ -303,6 +304,10 @@ class Kernels:
     def proj_wgrad_packed(self, dgates, xg, mask, dw_ih, P, T, B, Kp, K_dense, t_skip, ws):
         self._ck(self.lib.crvae_proj_wgrad_packed(ptr(dgates), ptr(xg), ptr(mask), ptr(dw_ih), P, T, B, Kp, K_dense, t_skip, ptr(ws),
                                                   stream_ptr()), "crvae_proj_wgrad_packed")
+
+    def ista_rows(self, w, dw, row_norm, rows, cols, lr, thr, do_prox):
+        self._ck(self.lib.crvae_ista_rows(ptr(w), ptr(dw), ptr(row_norm), rows, cols, float(lr), float(thr), int(do_prox), stream_ptr()),
+                 "crvae_ista_rows")
 
     def gen_scatter(self, y, noise, x, x_hi, x_lo, out, B, p, t, steps, base, rem, widest, scale):
         self._ck(self.lib.crvae_gen_scatter(ptr(y), ptr(noise), ptr(x), ptr(x_hi), ptr(x_lo), ptr(out), B, p, t, steps, base, rem,
