@@ -455,7 +455,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler: sampler.__enter__()
     ms_dev = timed(lambda i: run.iterate(eps_dev[i % n_eps]))
-    loss_t = eng.loss.clone()
+    loss_t = run.loss.clone()                   # completes the pending forward of the last flow replay
     if world > 1:
         dist.all_reduce(loss_t)                 # loss = sum over ALL heads: comparable across N
     loss_end = float(loss_t)
@@ -481,7 +481,10 @@ def run_ours(args):
     if world == 1 and not args.lean:
         extra["check_block"] = time_check_block(V, m, run, eps_dev)
     # CUDA graphs must be gone before anything is torn down
-    run.g_full = run.g_update = run.g_fwd = None
+    flow_info = {"enabled": run.g_flow is not None,
+                 "head_groups": [hi - lo for lo, hi in eng._flow["groups"]] if getattr(eng, "_flow", None) else None}
+    run.finish_forward()
+    run.g_full = run.g_update = run.g_fwd = run.g_flow = run.g_recupd = run.g_pre = run.g_rec = None
     torch.cuda.synchronize()
     parity = None
     if world > 1:
@@ -544,6 +547,7 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "cuda_graphs": not args.no_graphs, "l2_flush_between_steps": bool(flush),
+            "flow": flow_info,
             "clocks": sampler.summary() if sampler else None,
             "roofline": roofline, "roofline_all": roof_all, "stages_ms": {k: round(v["ms_per_step"], 4) for k, v in stages.items()},
             "tensor_peak": {k: pk[k] for k in ("tf32_tflops", "tf32_tflops_sustained", "how") if k in pk},

@@ -213,8 +213,9 @@ def test_cuda_graph_replay_equals_eager(traj):
         run.update(); run.forward(eps[1]); run.capture()
         for k in range(2, 8):
             run.iterate(eps[k])
-        finals.append((m.engine.theta.flat.clone(), float(m.engine.loss)))
+        finals.append((m.engine.theta.flat.clone(), float(run.loss), run.g_flow is not None))
     assert torch.equal(finals[0][0], finals[1][0]) and finals[0][1] == finals[1][1]     # deterministic kernels
+    assert not finals[0][2]
 
 
 def test_host_fed_iteration_equals_device_fed(traj):
@@ -239,7 +240,7 @@ def test_host_fed_iteration_equals_device_fed(traj):
                 slot = run.iterate_from_host(Xh, eps_h[k])
             else:
                 run.iterate(eps_h[k].cuda())
-                losses.append(float(m.engine.loss))
+                losses.append(float(run.loss))
         if host_fed:
             ring = run.losses_from_host()
             losses = [float(ring[i]) for i in range(6)]
@@ -862,3 +863,42 @@ def test_family_b_crvae_matches_reference():
     from tests.family_b_check import run
     m = run("cuda")
     assert m.theta.flat.is_cuda
+
+
+@pytest.mark.parametrize("p,groups", [(100, "auto"), (100, "74,26"), (100, "40,30,30"), (24, "auto")])
+def test_flow_iteration_equals_plain_iteration(p, groups):
+    """The software-pipelined iteration (engine.flow_body: [rec ; update ; pre] with the heads cut into stream groups,
+    captured into one CUDA graph) against the plain backward -> step -> forward sequence over 8 iterations, ridge and prox
+    active; at p = 100 with the automatic split and with forced splits, at p = 24 on the low-latency kernels (one group).
+    Same kernels on the same data; the gradient GEMMs cut their reduction by the number of heads they are given, so a
+    grouping changes the rounding of dW (not its value): weights agree to 1e-5, GC exactly, and a flow run repeated is
+    bit-identical (deterministic for a fixed grouping)."""
+    import vae_connexe_b200 as V
+    B = 256
+    gen = torch.Generator().manual_seed(3)
+    X = torch.randn(B, 20, p, generator=gen).cuda()
+    eps = [torch.randn(B, H, generator=gen).cuda() for _ in range(10)]
+    finals = []
+    for flow in (False, True, True):
+        os.environ["CRVAE_FLOW"] = "1" if flow else "0"
+        os.environ["CRVAE_GROUPS"] = groups
+        try:
+            torch.manual_seed(0)
+            m = V.CRVAE(p, np.ones((p, p)), 64)
+            run = V.Phase1Runner(m, X, 5e-2, 0.1, 0.01, 0.1, use_graphs=True)
+            run.forward(eps[0])
+            run.update(); run.forward(eps[1]); run.capture()
+            assert (run.g_flow is not None) == flow
+            losses = []
+            for k in range(2, 10):
+                run.iterate(eps[k])
+                if k in (4, 9):
+                    losses.append(float(run.loss))            # completes the pending forward (state P -> A), then continues
+            if flow and groups != "auto":
+                assert len(m.engine._flow["groups"]) == len(groups.split(","))
+            finals.append((m.engine.theta.flat.clone(), losses, m.GC().clone()))
+        finally:
+            del os.environ["CRVAE_FLOW"], os.environ["CRVAE_GROUPS"]
+    plain, flow1, flow2 = finals
+    assert _rel(flow1[0], plain[0]) < 1e-5 and np.allclose(flow1[1], plain[1], rtol=1e-5) and torch.equal(flow1[2], plain[2])
+    assert torch.equal(flow1[0], flow2[0]) and flow1[1] == flow2[1]

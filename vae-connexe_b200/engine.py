@@ -416,6 +416,208 @@ class CRVAEEngine:
             e.record()
             hook(s, e)
 
+    # ------------------------------------------------------------------ software-pipelined ("flow") iteration
+    # The steady-state iteration is a cycle  pre -> rec -> update -> pre -> ...  with
+    #     pre    = encoder chain (-> z) + per-head projection gi          (needs the updated weights)
+    #     rec    = decoder recurrence + MSE                              (needs gi and z)
+    #     update = BPTT, weight gradients, GD, prox                      (needs rec's activations)
+    # The only full barrier of the cycle sits between pre and rec (z depends on every head's dh0 through the encoder
+    # update).  flow_body() runs  rec ; update ; pre  as ONE unit in which the heads are cut into groups, each on its own
+    # stream:  recurrence(g) -> MSE(g) -> BPTT(g) -> dW_hh(g), dW_ih(g) -> prox(g) -> projection(g).  With 200 tiles on
+    # 148 SMs the recurrent kernels leave a tail wave of 52 tiles; grouped, the forward's tail overlaps the BPTT of the
+    # first group and the BPTT's tail overlaps the first group's gradient GEMMs, and every group's next projection
+    # overlaps the (latency-bound) encoder backward / forward chain on the side stream.  Captured into a CUDA graph by
+    # train.Phase1Runner; bit-identical to backward() + step() + forward() (same kernels on the same data).
+    def flow_supported(self) -> bool:
+        k = self.k
+        return (self.device.type == "cuda" and self.P > 0 and self.B is not None and self.B % 32 == 0 and not self.packed
+                and self.proj_mode == "tc3" and self.rec_mode in ("tc3", "ll") and self.bwd_mode == "defer"
+                and hasattr(k, "gru_dwhh_tc") and self.ws_lat is not None and self.use_side_stream)
+
+    def _flow_setup(self):
+        if getattr(self, "_flow", None) is not None and self._flow["B"] == self.B:
+            return self._flow
+        import os as _os
+        P, B, k, dev = self.P, self.B, self.k, self.device
+        spec = _os.environ.get("CRVAE_GROUPS", "auto")
+        if spec == "auto":
+            tiles = (B + 127) // 128
+            # two equal groups whenever the 128-row recurrent grid is more than one wave but not many: measured at p = 100
+            # (200 tiles, ms per iteration): one group 0.612, 74+26 0.549, 50+50 0.523, 34+33+33 0.543, 4x25 0.551, 5x20 0.557
+            sizes = [P // 2, P - P // 2] if (self.rec_mode == "tc3" and P >= 16 and 148 < P * tiles <= 4 * 148) else [P]
+        else:
+            sizes = [int(x) for x in spec.split(",") if x]
+            if sum(sizes) != P or min(sizes) <= 0:
+                sizes = [P]
+        groups, lo = [], 0
+        for n in sizes:
+            groups.append((lo, lo + n)); lo += n
+        zf = lambda n: torch.zeros(n // 4 + 4, dtype=torch.float32, device=dev)
+        ws = [dict(gru=zf(k.gru_bwd_workspace(hi - lo, B)), dwhh=zf(k.gru_dwhh_tc_workspace(hi - lo, DEC_STEPS, B)),
+                   wgrad=zf(k.proj_wgrad_tc_workspace(hi - lo, DEC_STEPS, B, self.p, 1))) for lo, hi in groups]
+        streams = [None] + [torch.cuda.Stream(device=dev) for _ in groups[1:]]
+        self._flow = dict(B=B, groups=groups, ws=ws, streams=streams)
+        return self._flow
+
+    def _flow_rec_group(self, lo, hi):
+        """Decoder recurrence + MSE of heads [lo, hi)."""
+        k, th, B = self.k, self.theta, self.B
+        n = hi - lo
+        sl = slice(lo, hi)
+        if self.rec_mode == "tc3":
+            k.gru_fwd_tc(self.gates[sl], th["b_ih"][sl], th["w_hh"][sl], None, th["b_hh"][sl], self.zlat, 0, th["w_lin"][sl],
+                         th["b_lin"][sl], self.hs[sl], self.ghn[sl], self.pred[sl], n, DEC_STEPS, B, 1)
+        else:
+            k.gru_fwd_ll(self.gates[sl], th["b_ih"][sl], th["w_hh"][sl], th["b_hh"][sl], self.zlat, 0, th["w_lin"][sl], th["b_lin"][sl],
+                         self.hs[sl], self.ghn[sl], self.pred[sl], n, DEC_STEPS, B, 1)
+        k.mse_fwd_bwd(self.pred[sl], self.target[sl], self.sse[sl], self.dpred[sl], None, n, DEC_STEPS, B)
+
+    def _flow_bwd_group(self, lo, hi, ws):
+        k, th, g, B = self.k, self.theta, self.grad, self.B
+        n, sl = hi - lo, slice(lo, hi)
+        fn = k.gru_bwd_tc if self.rec_mode == "tc3" else None
+        if fn is not None:
+            fn(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None,
+               g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
+        else:
+            k.gru_bwd_ll(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None, None,
+                         g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
+
+    def _flow_wgrads_group(self, lo, hi, ws, lam_ridge):
+        """dW_hh, dW_ih (+ ridge) of heads [lo, hi)."""
+        k, th, g, B, p_ = self.k, self.theta, self.grad, self.B, self.p
+        n, sl = hi - lo, slice(lo, hi)
+        mask = None if self.mask_u8 is None else self.mask_u8[sl]
+        k.gru_dwhh_tc(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, g["w_hh"][sl], n, DEC_STEPS, B, ws["dwhh"])
+        k.proj_wgrad_tc(self.gates[sl], self.dec_in_hi, self.dec_in_lo, mask, g["w_ih"][sl], n, DEC_STEPS, B, p_, 1, ws["wgrad"])
+        if lam_ridge != 0.0:
+            k.axpy(g["w_hh"][sl], th["w_hh"][sl], n * G * H, 2.0 * lam_ridge)
+            k.axpy(g["w_lin"][sl], th["w_lin"][sl], n * H, 2.0 * lam_ridge)
+
+    def _flow_prox_proj_group(self, lo, hi, lr, lam, with_proj):
+        """GD + prox of w_ih, GD of b_ih, then (with_proj) the NEXT iteration's projection of heads [lo, hi)."""
+        k, th, g, B, p_ = self.k, self.theta, self.grad, self.B, self.p
+        n, sl = hi - lo, slice(lo, hi)
+        mask = None if self.mask_u8 is None else self.mask_u8[sl]
+        k.gd_prox_gc(th["w_ih"][sl], g["w_ih"][sl], mask, self.col_norm[sl], n, self.Kw, _f32(lr), _f32(lam * lr), lam > 0)
+        k.gd_step(th["b_ih"][sl], g["b_ih"][sl], n * G, _f32(lr))         # the projection adds b_ih: updated per group, not by the big GD
+        if with_proj:
+            k.split_tf32_gate_rows(th["w_ih"][sl], self.w_ih_hi[sl], self.w_ih_lo[sl], n * G, p_)
+            k.proj_fwd_tc(self.dec_in_hi, self.dec_in_lo, self.w_ih_hi[sl], self.w_ih_lo[sl], th["b_ih"][sl], self.gates[sl], n, DEC_STEPS,
+                          B, p_, 1)
+
+    def _flow_gd_rest(self, lr):
+        """GD on everything but w_ih and the heads' b_ih (both updated per group): w_hh | [b_ih] | b_hh ... encoder."""
+        k, th, g = self.k, self.theta, self.grad
+        o_whh, o_bih, o_bhh = self.theta.offsets["w_hh"], self.theta.offsets["b_ih"], self.theta.offsets["b_hh"]
+        k.gd_step(th.flat[o_whh:o_bih], g.flat[o_whh:o_bih], o_bih - o_whh, _f32(lr))
+        k.gd_step(th.flat[o_bhh:], g.flat[o_bhh:], self.theta.numel - o_bhh, _f32(lr))
+
+    def _enc_forward_chain(self):
+        k, th, B = self.k, self.theta, self.B
+        self._project(self.enc_in, "enc", th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, ENC_STEPS, 0)
+        R.gru_forward_small(k, self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
+                            self.enc_hs, self.enc_ghn, None, 1, ENC_STEPS, B, 0)
+        k.latent_head_fwd(self.enc_hs[0, ENC_STEPS - 1], th["lat_w"], th["lat_b"], self.eps, self.lat, self.zlat, self.kl, B,
+                          self.kl_form, self.ws_lat)
+
+    def _enc_backward_chain(self, beta):
+        k, th, g, B, P, p_ = self.k, self.theta, self.grad, self.B, self.P, self.p
+        if self.comm is not None:
+            k.latent_bwd(self.dh0, P, None, None, None, 0.0, self.kl_form, None, self.dz_part, B)
+            self._allreduce_dz()
+            k.latent_bwd(None, 0, self.dz_part, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+        else:
+            k.latent_bwd(self.dh0, P, None, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+        k.latent_head_bwd(self.dlat, self.enc_hs[0, ENC_STEPS - 1], th["lat_w"], g["lat_w"], g["lat_b"], self.dhT, B)
+        R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
+                             None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
+                             1, ENC_STEPS, B, self.ws_gru_enc, self.ws_dwhh_enc)
+        if self.enc_tc and self.ws_wgrad_tc_enc is not None:
+            k.proj_wgrad_tc(self.enc_gates, self.enc_in_hi, self.enc_in_lo, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad_tc_enc)
+        else:
+            k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
+
+    def flow_pre(self):
+        """pre: encoder chain on the staged noise (eps_next) + every head's projection, for the CURRENT weights."""
+        fl = self._flow_setup()
+        th, k, p_ = self.theta, self.k, self.p
+        self.eps.copy_(self.eps_next)
+        side = self._fork()
+        with self._on(side):
+            self._enc_forward_chain()
+        k.split_tf32_gate_rows(th["w_ih"], self.w_ih_hi, self.w_ih_lo, self.P * G, p_)
+        k.proj_fwd_tc(self.dec_in_hi, self.dec_in_lo, self.w_ih_hi, self.w_ih_lo, th["b_ih"], self.gates, self.P, DEC_STEPS, self.B, p_, 1)
+        self._join(side)
+
+    def flow_rec(self):
+        """rec alone (completes a forward whose pre ran earlier): recurrences + MSE + loss."""
+        fl = self._flow_setup()
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event(); start.record(main)
+        evs = []
+        for (lo, hi), st in zip(fl["groups"], fl["streams"]):
+            if st is None:
+                self._flow_rec_group(lo, hi)
+            else:
+                st.wait_event(start)
+                with torch.cuda.stream(st):
+                    self._flow_rec_group(lo, hi)
+                    e = torch.cuda.Event(); e.record(st); evs.append(e)
+        for e in evs:
+            main.wait_event(e)
+        self.k.dot_small(self.sse, self.P, 1.0 / (DEC_STEPS * self.B), self.loss)
+
+    def flow_body(self, lr: float, lam: float, lam_ridge: float, beta: float, with_pre: bool = True):
+        """rec ; update ; (pre)  as one software-pipelined unit (see the section comment).  Expects the state left by
+        flow_pre(): gi in the gate buffer, z in zlat.  with_pre=False stops after the update (a batch re-bind or a check
+        block follows)."""
+        fl = self._flow_setup()
+        k = self.k
+        main = torch.cuda.current_stream()
+        side = self._side if self._side is not None else torch.cuda.Stream(device=self.device, priority=-1)
+        self._side = side
+        start = torch.cuda.Event(); start.record(main)
+        side.wait_event(start)
+        ev_mse, ev_bwd, ev_grad, ev_done = [], [], [], []
+        for gi_, ((lo, hi), st) in enumerate(zip(fl["groups"], fl["streams"])):
+            ctx = torch.cuda.stream(st) if st is not None else self._on(None)
+            if st is not None:
+                st.wait_event(start)
+            with ctx:
+                cur = st if st is not None else main
+                self._flow_rec_group(lo, hi)
+                e = torch.cuda.Event(); e.record(cur); ev_mse.append(e)
+                self._flow_bwd_group(lo, hi, fl["ws"][gi_])
+                e = torch.cuda.Event(); e.record(cur); ev_bwd.append(e)
+        # encoder backward chain needs every group's dh0
+        with torch.cuda.stream(side):
+            for e in ev_mse:
+                side.wait_event(e)
+            k.dot_small(self.sse, self.P, 1.0 / (DEC_STEPS * self.B), self.loss)       # loss of the forward just completed
+            for e in ev_bwd:
+                side.wait_event(e)
+            self._enc_backward_chain(beta)
+        for gi_, ((lo, hi), st) in enumerate(zip(fl["groups"], fl["streams"])):
+            ctx = torch.cuda.stream(st) if st is not None else self._on(None)
+            with ctx:
+                cur = st if st is not None else main
+                self._flow_wgrads_group(lo, hi, fl["ws"][gi_], lam_ridge)
+                e = torch.cuda.Event(); e.record(cur); ev_grad.append(e)
+                self._flow_prox_proj_group(lo, hi, lr, lam, with_pre)
+                e = torch.cuda.Event(); e.record(cur); ev_done.append(e)
+        with torch.cuda.stream(side):
+            for e in ev_grad:                      # w_hh gradients of every group; also: every reader of z (dW_hh) is done
+                side.wait_event(e)
+            self._flow_gd_rest(lr)
+            if with_pre:
+                self.eps.copy_(self.eps_next)
+                self._enc_forward_chain()
+            e_side = torch.cuda.Event(); e_side.record(side)
+        for e in ev_done:
+            main.wait_event(e)
+        main.wait_event(e_side)
+
     # ------------------------------------------------------------------ update
     def step(self, lr: float, lam: float):
         """GD on every parameter (:498-499) + group-lasso prox on the heads' w_ih (:502-504)."""

@@ -59,14 +59,32 @@ class Phase1Runner:
         self.eng.bind_batch(Xb)
         self.use_graphs = use_graphs
         self.g_full = self.g_update = self.g_fwd = None
+        # software-pipelined iteration (engine.flow_body): graphs of [rec ; update ; pre], [rec ; update], [pre], [rec].
+        # state "A": a forward is complete (activations + loss valid); state "P": only its pre half ran (gi and z are
+        # ready, the recurrence is pending) -- the state the flow graph starts from and ends in.
+        import os as _os
+        self.use_flow = use_graphs and _os.environ.get("CRVAE_FLOW", "1") != "0"
+        self.g_flow = self.g_recupd = self.g_pre = self.g_rec = None
+        self.state = "A"
 
     # eager pieces ------------------------------------------------------------------------------
     def forward(self, eps: Optional[torch.Tensor]):
         self.eng.forward(eps)
+        self.state = "A"
 
     def update(self):
+        self.finish_forward()
         self.eng.backward(self.beta, self.lam_ridge)
         self.eng.step(self.lr, self.lam)
+
+    def finish_forward(self):
+        """State P -> A: run the pending recurrence + loss of a forward whose pre half ran inside a flow replay."""
+        if self.state == "P":
+            if self.g_rec is not None:
+                self.g_rec.replay()
+            else:
+                self.eng.flow_rec()
+            self.state = "A"
 
     # graph capture -------------------------------------------------------------------------------
     def capture(self):
@@ -87,20 +105,50 @@ class Phase1Runner:
             pool = g.pool()
             graphs.append(g)
         self.g_update, self.g_fwd, self.g_full = graphs
+        if self.use_flow and self.eng.flow_supported():
+            eng = self.eng
+            eng._flow_setup()                 # streams / workspaces exist before the capture
+            bodies = (lambda: eng.flow_body(self.lr, self.lam, self.lam_ridge, self.beta, True),
+                      lambda: eng.flow_body(self.lr, self.lam, self.lam_ridge, self.beta, False),
+                      eng.flow_pre, eng.flow_rec)
+            flow_graphs = []
+            for body in bodies:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    body()
+                pool = g.pool()
+                flow_graphs.append(g)
+            self.g_flow, self.g_recupd, self.g_pre, self.g_rec = flow_graphs
         torch.cuda.synchronize()
         self.eng.restore(snap)              # capture does not execute, but stay defensive
 
     def forward_noeps(self):
         self.eng.forward_staged()
+        self.state = "A"
 
     def iterate(self, eps: torch.Tensor):
-        """One steady-state iteration (:497-515): backward, GD, prox, then forward with `eps`."""
+        """One steady-state iteration (:497-515): backward, GD, prox, then forward with `eps`.  With the flow graphs the
+        forward is left half done (state P: its recurrence runs at the start of the next iteration, overlapped with that
+        iteration's backward); finish_forward() -- called by everything that reads activations or the loss -- completes it."""
         self.eng.eps_next.copy_(eps, non_blocking=True)
-        if self.g_full is not None:
+        if self.g_flow is not None:
+            if self.state == "P":
+                self.g_flow.replay()
+            else:
+                self.g_update.replay()
+                self.g_pre.replay()
+            self.state = "P"
+        elif self.g_full is not None:
             self.g_full.replay()
         else:
             self.update()
             self.forward_noeps()
+
+    @property
+    def loss(self) -> torch.Tensor:
+        """Loss of the most recent forward (completes it first when it is pending)."""
+        self.finish_forward()
+        return self.eng.loss
 
     # ------------------------------------------------------------------ host-fed pipeline
     def iterate_from_host(self, X_host: torch.Tensor, eps_host: torch.Tensor) -> int:
@@ -130,21 +178,45 @@ class Phase1Runner:
         # Order matters: the backward of the PREVIOUS forward still reads the batch it was computed on (the weight
         # gradients multiply dgates by enc_in / dec_in), so the update runs first, THEN the new batch is bound, THEN
         # the forward -- exactly the reference's order when its loop resamples (CR-CS-RAE.py:557-558 precede the forward).
-        self.run_update()
-        cur.wait_event(st["copied"][j])
-        self.eng.bind_batch(st["X"][j])
-        self.run_forward(st["eps"][j])
-        st["consumed"][j].record(cur)
         slot = i % st["loss"].numel()
-        st["loss"][slot:slot + 1].copy_(self.eng.loss, non_blocking=True)
+        if self.g_flow is not None:
+            # flow form: [rec of the previous forward ; update] -> bind -> [pre]; this step's recurrence (and loss) runs at
+            # the start of the next call, overlapped with its backward, so the loss reaches its ring slot one call later
+            if self.state == "P":
+                self.g_recupd.replay()
+                prev = st.get("pending")
+                if prev is not None:
+                    st["loss"][prev:prev + 1].copy_(self.eng.loss, non_blocking=True)
+            else:
+                self.g_update.replay()
+            cur.wait_event(st["copied"][j])
+            self.eng.bind_batch(st["X"][j])
+            self.eng.eps_next.copy_(st["eps"][j], non_blocking=True)
+            self.g_pre.replay()
+            self.state = "P"
+            st["pending"] = slot
+        else:
+            self.run_update()
+            cur.wait_event(st["copied"][j])
+            self.eng.bind_batch(st["X"][j])
+            self.run_forward(st["eps"][j])
+            st["loss"][slot:slot + 1].copy_(self.eng.loss, non_blocking=True)
+        st["consumed"][j].record(cur)
         st["i"] = i + 1
         return slot
 
     def losses_from_host(self) -> torch.Tensor:
+        st = self._host
+        if self.state == "P":
+            self.finish_forward()
+            if st.get("pending") is not None:
+                st["loss"][st["pending"]:st["pending"] + 1].copy_(self.eng.loss, non_blocking=True)
+                st["pending"] = None
         torch.cuda.synchronize(self.eng.device)
-        return self._host["loss"]
+        return st["loss"]
 
     def run_update(self):
+        self.finish_forward()
         if self.g_update is not None:
             self.g_update.replay()
         else:
@@ -154,6 +226,7 @@ class Phase1Runner:
         self.eng.eps_next.copy_(eps, non_blocking=True)
         if self.g_fwd is not None:
             self.g_fwd.replay()
+            self.state = "A"
         else:
             self.forward_noeps()
 
@@ -197,7 +270,7 @@ def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0,
         if check:
             eps_check = feed.next()                               # :522 draw
             h0_gen = feed.next()                                  # :550 -> :225 generation draw
-        run.run_update()                                          # :497-506
+        run.run_update()                                          # :497-506 (completes a pending flow forward first)
         if check:
             # The check-block forward (:522) and the training forward (:508) use the same weights,
             # so they are evaluated in the opposite order: the activations left in the engine are
@@ -238,6 +311,7 @@ def train_phase1(crvae, X, context, lr, max_iter, lam=0, lam_ridge=0,
         if mean_loss < best_loss:                                 # :544-547
             best_loss, best_it = mean_loss, it
             best_snap = eng.snapshot()
+    run.finish_forward()
     if best_snap is not None:                                     # :558 restore best model
         eng.restore(best_snap)
     crvae.best_it = best_it
