@@ -278,6 +278,17 @@ size_t crvae_proj_wgrad_packed_workspace(int P, int T, int B, int Kp, int K_dens
 int crvae_proj_wgrad_packed(const float* dgates, const float* xg, const uint8_t* mask, float* dw_ih,
                             int P, int T, int B, int Kp, int K_dense, int t_skip, void* workspace, void* stream);
 
+/* Head-sharded training, the one data-path collective: dz = sum over ALL heads of dh0, needed by the
+ * replicated encoder.  One kernel = local head sum + one-shot all-reduce over NVLink peer memory + the latent backward
+ * (crvae_latent_bwd's arithmetic) in its epilogue.  peer_bufs[r] = rank r's SYMMETRIC buffer of crvae_dz_allreduce_bytes()
+ * bytes as mapped into THIS process (e.g. torch.distributed._symmetric_memory rendezvous: buffer_ptrs); the buffers must
+ * be zero before the first call on any rank.  Partials are summed in rank order on every rank: bit-identical results
+ * everywhere.  Re-launchable back to back (epochs + two slots), CUDA-graph capturable, no NCCL involved.            */
+size_t crvae_dz_allreduce_bytes(int B, int Z, int world);
+int crvae_dz_allreduce_latent_bwd(const float* dh0, int P, void* const* peer_bufs, int rank, int world, const float* lat,
+                                  const float* eps, float beta, int kl_form, float* dlat, float* dz_out, int B, int Z,
+                                  void* stream);
+
 /* Family-B CR-VAE (CRVAE.py:134-150): ISTA step on the per-head input maps W_in[i] (D x H), one group per ROW
  * (= one candidate parent series):  W_tmp = W - lr*dW;  W <- W_tmp * max(1 - thr/||W_tmp[row,:]||_2, 0)  with thr = lr*lambda
  * (a zero row stays zero, as in the reference: 1 - thr/0 = -inf -> 0).  w / dw [rows, cols] row-major; row_norm [rows]

@@ -33,6 +33,7 @@ def main():
     ph2 = np.load(os.path.join(ROOT, "tests", "golden", "p10_phase2.npz"))
     Xt = torch.from_numpy(traj["data"].T.copy())[None].cuda()
     ok = True
+    closers = []
 
     def run(sharded, phase):
         torch.manual_seed(0); np.random.seed(0)
@@ -40,10 +41,12 @@ def main():
         log = []
         if phase == 1:
             m = V.CRVAE(10, np.ones((10, 10)), 64, **kw)
+            closers.append(m)
             V.train_phase1(m, Xt, context=20, lam=0.1, lam_ridge=0.01, lr=5e-2, max_iter=61, check_every=20, verbose=0, log=log,
                            use_graphs=not (one_gpu and sharded))
             return m, None, log
         m = V.CRVAE(10, ph2["connection"], 64, **kw)
+        closers.append(m)
         v = V.VRAE4E(10, 64)
         V.train_phase2(m, v, Xt, context=20, lam=0., lam_ridge=0, lr=5e-2, max_iter=21, check_every=10, verbose=0, log=log,
                        use_graphs=not (one_gpu and sharded))
@@ -87,6 +90,7 @@ def main():
         torch.manual_seed(0); np.random.seed(0)
         kw = dict(rank=rank, world_size=world, group=dist.group.WORLD) if sharded else {}
         m = V.CRVAE(p_tc, np.ones((p_tc, p_tc)), 64, **kw)
+        closers.append(m)
         log = []
         V.train_phase1(m, Xtc, context=20, lam=0.1, lam_ridge=0.0, lr=5e-2, max_iter=41, check_every=20, verbose=0, log=log,
                        use_graphs=not (one_gpu and sharded))
@@ -112,7 +116,16 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("DIST_PARITY", "PASS" if flag.item() == 1.0 else "FAIL", f"world={world}")
+        print("DIST_PARITY", "PASS" if flag.item() == 1.0 else "FAIL", f"world={world}", flush=True)
+    # orderly teardown: captured graphs that contain collectives (the sharded generator) and the peer-memory communicator go
+    # first, then the process group
+    import gc
+    for mdl in closers:
+        mdl.close()
+    del closers[:]
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 

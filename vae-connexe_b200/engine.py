@@ -195,6 +195,9 @@ class CRVAEEngine:
         P, dev = self.P, self.device
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         self.B = B
+        if self.comm is not None and self.group is not None:      # the fused peer-memory dz all-reduce needs the batch size
+            from .sharding import make_dz_comm
+            self.comm = make_dz_comm(self.k, self.group, B, H, dev, self.comm)
         self.gates = z(max(P, 1), DEC_STEPS, B, G)
         self.hs = z(max(P, 1), DEC_STEPS, B, H)
         self.ghn = z(max(P, 1), DEC_STEPS, B, H)
@@ -365,12 +368,7 @@ class CRVAEEngine:
         side = self._fork()
         with self._on(side):
             # dz = sum over ALL heads of dh0 (every head's h0 is z, :218)
-            if self.comm is not None:
-                k.latent_bwd(self.dh0 if P > 0 else None, P, None, None, None, 0.0, self.kl_form, None, self.dz_part, B)
-                self._allreduce_dz()
-                k.latent_bwd(None, 0, self.dz_part, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
-            else:
-                k.latent_bwd(self.dh0, P, None, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+            self._dz_latent_bwd(beta)
             if dlat_extra is not None:
                 k.axpy(self.dlat, dlat_extra, B * 2 * H, 1.0)
             hT = self.enc_hs[0, ENC_STEPS - 1]
@@ -404,6 +402,25 @@ class CRVAEEngine:
                 k.axpy(g["w_hh"], th["w_hh"], P * G * H, 2.0 * lam_ridge)
                 k.axpy(g["w_lin"], th["w_lin"], P * H, 2.0 * lam_ridge)
         self._join(side)
+
+    def _dz_latent_bwd(self, beta):
+        """dz = sum over ALL heads of dh0 (every head's h0 is z, :218) -> gradient into [mu | log_var].  On a head shard the
+        sum crosses ranks: one fused kernel over NVLink peer memory (sharding.SymmComm) or sum -> NCCL all-reduce -> pointwise."""
+        k, B, P = self.k, self.B, self.P
+        if self.comm is None:
+            k.latent_bwd(self.dh0, P, None, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+        elif getattr(self.comm, "fused", False):
+            hook = getattr(self, "_stage_hook", None)
+            if hook is not None:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+            self.comm.latent_bwd(self.dh0 if P > 0 else None, P, self.lat, self.eps, beta, self.kl_form, self.dlat, B)
+            if hook is not None:
+                e.record(); hook(s, e)
+        else:
+            k.latent_bwd(self.dh0 if P > 0 else None, P, None, None, None, 0.0, self.kl_form, None, self.dz_part, B)
+            self._allreduce_dz()
+            k.latent_bwd(None, 0, self.dz_part, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
 
     def _allreduce_dz(self):
         """Sum of dz_part over the head shards (the one data-path collective)."""
@@ -523,12 +540,7 @@ class CRVAEEngine:
 
     def _enc_backward_chain(self, beta):
         k, th, g, B, P, p_ = self.k, self.theta, self.grad, self.B, self.P, self.p
-        if self.comm is not None:
-            k.latent_bwd(self.dh0, P, None, None, None, 0.0, self.kl_form, None, self.dz_part, B)
-            self._allreduce_dz()
-            k.latent_bwd(None, 0, self.dz_part, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
-        else:
-            k.latent_bwd(self.dh0, P, None, self.lat, self.eps, beta, self.kl_form, self.dlat, None, B)
+        self._dz_latent_bwd(beta)
         k.latent_head_bwd(self.dlat, self.enc_hs[0, ENC_STEPS - 1], th["lat_w"], g["lat_w"], g["lat_b"], self.dhT, B)
         R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
                              None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,

@@ -65,6 +65,9 @@ SIGNATURES = {
     "crvae_proj_fwd_packed": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p]),
     "crvae_proj_wgrad_packed_workspace": (_c_size_t, [_c_int] * 5),
     "crvae_proj_wgrad_packed": (_c_int, [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p, _c_void_p]),
+    "crvae_dz_allreduce_bytes": (_c_size_t, [_c_int] * 3),
+    "crvae_dz_allreduce_latent_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_float, _c_int,
+                                              _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "crvae_ista_rows": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_int, _c_float, _c_float, _c_int, _c_void_p]),
     "crvae_gen_scatter": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_float, _c_void_p]),
     "crvae_sumsq": (_c_int, [_c_void_p, _c_i64, _c_void_p, _c_void_p]),
@@ -304,6 +307,14 @@ class Kernels:
     def proj_wgrad_packed(self, dgates, xg, mask, dw_ih, P, T, B, Kp, K_dense, t_skip, ws):
         self._ck(self.lib.crvae_proj_wgrad_packed(ptr(dgates), ptr(xg), ptr(mask), ptr(dw_ih), P, T, B, Kp, K_dense, t_skip, ptr(ws),
                                                   stream_ptr()), "crvae_proj_wgrad_packed")
+
+    def dz_allreduce_bytes(self, B, Z, world) -> int:
+        return int(self.lib.crvae_dz_allreduce_bytes(B, Z, world))
+
+    def dz_allreduce_latent_bwd(self, dh0, P, peer_ptrs, rank, world, lat, eps, beta, kl_form, dlat, dz_out, B, Z=64):
+        arr = (C.c_void_p * world)(*[int(x) for x in peer_ptrs])
+        self._ck(self.lib.crvae_dz_allreduce_latent_bwd(ptr(dh0), P, arr, rank, world, ptr(lat), ptr(eps), float(beta), kl_form,
+                                                        ptr(dlat), ptr(dz_out), B, Z, stream_ptr()), "crvae_dz_allreduce_latent_bwd")
 
     def ista_rows(self, w, dw, row_norm, rows, cols, lr, thr, do_prox):
         self._ck(self.lib.crvae_ista_rows(ptr(w), ptr(dw), ptr(row_norm), rows, cols, float(lr), float(thr), int(do_prox), stream_ptr()),

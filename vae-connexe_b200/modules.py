@@ -257,6 +257,17 @@ class CRVAE(nn.Module):
         self._bwd_ran = False
         self._ridge_pending.clear()
 
+    def close(self):
+        """Drop everything that holds communicator state: the generator's captured CUDA graphs (they contain the per-step
+        all-gather on a head shard) and the dz communicator.  Call before torch.distributed.destroy_process_group():
+        tearing the communicator down while a captured graph still references its kernels hangs."""
+        plans = self.__dict__.get("_gen_plans")
+        if plans:
+            for plan in plans.values():
+                plan.graph = None
+            plans.clear()
+        self.engine.close()
+
     def _sync_ragged_grads(self):
         return None                        # masked-dense: gradients of structural zeros are already masked
 

@@ -65,3 +65,54 @@ class TorchComm:
 
     def close(self) -> None:
         return None
+
+
+class SymmComm:
+    """dz all-reduce as ONE kernel over NVLink peer memory (csrc/dz_allreduce.cu): local head sum + one-shot all-reduce +
+    latent backward.  torch.distributed._symmetric_memory supplies the plumbing only -- a buffer with the same layout on
+    every rank and the peers' mappings of it; the exchange itself is P2P stores / loads issued by our kernel."""
+
+    fused = True
+
+    def __init__(self, k, group, B: int, Z: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.k, self.group = k, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        n = k.dz_allreduce_bytes(B, Z, self.world) // 4
+        self.buf = symm_mem.empty(n, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        self.buf.zero_()                                   # flags / epochs start at zero on every rank ...
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                # ... before any rank's first kernel can signal a peer
+        self.B, self.Z = B, Z
+
+    def latent_bwd(self, dh0, P, lat, eps, beta, kl_form, dlat, B):
+        self.k.dz_allreduce_latent_bwd(dh0, P, self.ptrs, self.rank, self.world, lat, eps, beta, kl_form, dlat, None, B, self.Z)
+
+    def allreduce_dz(self, dz_part: torch.Tensor) -> None:
+        dist.all_reduce(dz_part, op=dist.ReduceOp.SUM, group=self.group)
+
+    def close(self) -> None:
+        self.hdl = None
+        self.buf = None
+
+
+def make_dz_comm(k, group, B: int, Z: int, device, current):
+    """Upgrade the NCCL dz all-reduce to the fused peer-memory kernel when the ranks sit on NVLink-connected GPUs under the
+    NCCL backend; every rank takes the same decision (a failed rendezvous on any rank keeps NCCL everywhere)."""
+    import os
+    if not isinstance(current, TorchComm) or os.environ.get("CRVAE_DZ", "symm") != "symm" or not hasattr(k, "dz_allreduce_latent_bwd"):
+        return current
+    if torch.device(device).type != "cuda" or dist.get_backend(group) != "nccl":
+        return current
+    comm, ok = None, 1.0
+    try:
+        comm = SymmComm(k, group, B, Z, device)
+    except Exception as exc:                               # symmetric memory unavailable (no P2P / fabric): keep NCCL
+        ok = 0.0
+        import warnings
+        warnings.warn(f"symmetric-memory dz all-reduce unavailable ({exc!r}); using NCCL")
+    flag = torch.tensor([ok], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return comm if float(flag) == 1.0 else current
