@@ -194,7 +194,7 @@ STAGE_FNS = ["proj_fwd", "proj_fwd_tc", "split_tf32", "split_tf32_gate_rows", "p
              "gru_dwhh_tc", "gru_fwd", "gemm", "latent_fwd", "latent_head_fwd", "latent_head_bwd", "mse_fwd_bwd", "dot_small", "gru_bwd",
              "proj_wgrad", "latent_bwd", "gd_prox_gc", "gd_step", "axpy", "gru_fwd_ll", "gru_bwd_ll", "dz_allreduce", "enc_chain_fwd"]
 P_ARG = {"proj_fwd": 4, "gru_fwd": 11, "gru_bwd": 16, "proj_wgrad": 4, "proj_fwd_tc": 6, "proj_wgrad_tc": 5, "gru_fwd_tc": 12,
-         "gru_bwd_deferred": 15, "gru_bwd_tc": 14, "gru_dwhh_tc": 6, "gru_fwd_ll": 11, "gru_bwd_ll": 16}
+         "gru_bwd_deferred": 15, "gru_bwd_tc": 14, "gru_dwhh_tc": 6, "gru_fwd_ll": 11, "gru_bwd_ll": 15}
 
 
 def profile_stages(run, eps_list, reps):
