@@ -40,6 +40,14 @@ class _Engine:
         self.n_trainable = self.theta.offsets["start_token"]      # start_token never gets a gradient under TF = 1
         self.shape = None
 
+    @staticmethod
+    def _row_splits(rows: int) -> int:
+        """Chunks a long row reduction is cut into: the largest power of two <= 512 that divides `rows` and leaves >= 512 rows per chunk."""
+        s = 1
+        while s < 512 and rows % (2 * s) == 0 and rows // (2 * s) >= 512:
+            s *= 2
+        return s
+
     def bind(self, x: torch.Tensor):
         B, T, D = x.shape
         if self.shape != (B, T):
@@ -55,8 +63,10 @@ class _Engine:
             self.pre0, self.h0, self.dh0, self.dpre0 = z(B, H), z(B, H), z(1, B, H), z(B, H)
             self.pre, self.recon, self.drecon, self.dpre = z(T, B, D), z(T, B, D), z(T, B, D), z(T, B, D)
             self.dhT, self.enc_dh0 = z(1, B, H), z(1, B, H)
-            self.sse, self.kl = z(1), z(1)
+            self.sse, self.kl, self.sse_t = z(1), z(1), z(T)
             self.ones_B, self.ones_TB = torch.ones(B, 1, device=dev), torch.ones(T * B, 1, device=dev)
+            S = self._row_splits(T * B)
+            self.ones_S, self.part_w, self.part_b = torch.ones(1, S, device=dev), z(S, D, H), z(S, D)
             k = self.k
             self.ws_gru = torch.zeros(k.gru_bwd_workspace(1, B) // 4 + 4, dtype=torch.float32, device=dev)
             n = R.dwhh_workspace(k, 1, T, B)
@@ -82,14 +92,25 @@ class _Engine:
         k.gemm(L.GEMM_NT, 1, T * B, D, H, self.dec_hs, H, 0, th["out_w"], H, 0, self.pre, D, 0, th["out_b"], 0)
         k.act_fwd(self.pre, self.recon, T * B * D, self.act)                                                     # :91
         # rec_loss = SSE / batch (:143): sse over everything, d(recon) = 2*(recon - x)/B
-        k.mse_fwd_bwd(self.recon, self.xin, self.sse, self.drecon, None, 1, T, B * D, 2.0 / B)
+        k.mse_fwd_bwd(self.recon, self.xin, self.sse_t, self.drecon, None, T, 1, B * D, 2.0 / B)      # one CTA per timestep
+        k.dot_small(self.sse_t, T, 1.0, self.sse)
 
     def backward(self, beta: float):
         k, th, g, B, T, D, Z = self.k, self.theta, self.grad, self.B, self.T, self.D, self.Z
         TB = T * B
         k.act_bwd(self.drecon, self.recon, self.dpre, TB * D, self.act)
-        k.gemm(L.GEMM_TN, 1, D, H, TB, self.dpre, D, 0, self.dec_hs, H, 0, g["out_w"], H, 0)
-        k.gemm(L.GEMM_TN, 1, 1, D, TB, self.ones_TB, 1, 0, self.dpre, D, 0, g["out_b"], D, 0)
+        # fc_out gradients: reductions over T*B rows (524,288 at the config-4 size).  One GEMM would walk them in ONE CTA
+        # (16+ ms each); cut into S row chunks as a batched GEMM (S CTAs) + a [1 x S] . [S x D*H] GEMM that adds the partials
+        S = self._row_splits(TB)
+        if S > 1:
+            rows = TB // S
+            k.gemm(L.GEMM_TN, S, D, H, rows, self.dpre, D, rows * D, self.dec_hs, H, rows * H, self.part_w, H, D * H)
+            k.gemm(L.GEMM_NN, 1, 1, D * H, S, self.ones_S, S, 0, self.part_w, D * H, 0, g["out_w"], D * H, 0)
+            k.gemm(L.GEMM_TN, S, 1, D, rows, self.ones_TB, 1, rows, self.dpre, D, rows * D, self.part_b, D, D)
+            k.gemm(L.GEMM_NN, 1, 1, D, S, self.ones_S, S, 0, self.part_b, D, 0, g["out_b"], D, 0)
+        else:
+            k.gemm(L.GEMM_TN, 1, D, H, TB, self.dpre, D, 0, self.dec_hs, H, 0, g["out_w"], H, 0)
+            k.gemm(L.GEMM_TN, 1, 1, D, TB, self.ones_TB, 1, 0, self.dpre, D, 0, g["out_b"], D, 0)
         k.gemm(L.GEMM_NN, 1, TB, H, D, self.dpre, D, 0, th["out_w"], H, 0, self.dhs, H, 0)
         R.gru_backward_small(k, self.dec_gates, self.dec_ghn, self.dec_hs, self.h0, 0, th["dec_w_hh"], None, None, None, self.dhs,
                              g["dec_w_hh"].view(1, G, H), g["dec_b_hh"], g["dec_b_ih"], None, None, self.dh0, 1, T, B, self.ws_gru,
