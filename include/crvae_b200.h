@@ -289,6 +289,13 @@ int crvae_dz_allreduce_latent_bwd(const float* dh0, int P, void* const* peer_buf
                                   const float* eps, float beta, int kl_form, float* dlat, float* dz_out, int B, int Z,
                                   void* stream);
 
+/* MixtureCSRAE (CSRAE_new.py:113-150), the Bernoulli reconstruction term: sum_out[0] = sum over n elements of
+ * binary_cross_entropy_with_logits(logits, x); dlogits (optional) = (sigmoid(logits) - x) * dscale.  workspace >=
+ * crvae_bce_logits_workspace(n) bytes (per-CTA fp64 partials, added in CTA order).                                  */
+size_t crvae_bce_logits_workspace(int64_t n);
+int crvae_bce_logits_fwd_bwd(const float* logits, const float* x, float* sum_out, float* dlogits, int64_t n, float dscale,
+                             void* workspace, void* stream);
+
 /* Family-B CR-VAE (CRVAE.py:134-150): ISTA step on the per-head input maps W_in[i] (D x H), one group per ROW
  * (= one candidate parent series):  W_tmp = W - lr*dW;  W <- W_tmp * max(1 - thr/||W_tmp[row,:]||_2, 0)  with thr = lr*lambda
  * (a zero row stays zero, as in the reference: 1 - thr/0 = -inf -> 0).  w / dw [rows, cols] row-major; row_norm [rows]

@@ -252,6 +252,16 @@ class OracleKernels:
         dst.reshape(-1)[: rows * cols].view(cols, rows).copy_(src.reshape(-1)[: rows * cols].view(rows, cols).t())
         self.launches += 1
 
+    def bce_logits_workspace(self, n):
+        return 16
+
+    def bce_logits_fwd_bwd(self, logits, x, sum_out, dlogits, n, dscale, ws):
+        l, t = logits.reshape(-1)[:n], x.reshape(-1)[:n]
+        sum_out[0] = torch.nn.functional.binary_cross_entropy_with_logits(l, t, reduction="sum")
+        if dlogits is not None:
+            dlogits.reshape(-1)[:n] = (torch.sigmoid(l) - t) * dscale
+        self.launches += 1
+
     def ista_rows(self, w, dw, row_norm, rows, cols, lr, thr, do_prox):
         wv = w.reshape(-1)[: rows * cols].view(rows, cols)
         tmp = wv if dw is None else wv - torch.tensor(lr, dtype=torch.float32) * dw.reshape(-1)[: rows * cols].view(rows, cols)

@@ -902,3 +902,10 @@ def test_flow_iteration_equals_plain_iteration(p, groups):
     plain, flow1, flow2 = finals
     assert _rel(flow1[0], plain[0]) < 1e-5 and np.allclose(flow1[1], plain[1], rtol=1e-5) and torch.equal(flow1[2], plain[2])
     assert torch.equal(flow1[0], flow2[0]) and flow1[1] == flow2[1]
+
+
+def test_mixture_csrae_matches_reference():
+    """MixtureCSRAE (reference CSRAE_new.py:113-150; MLP auto-encoder + BCE + CS divergence to a GMM prior, latent
+    space embedded in the 64-dimension divergence kernel) on the CUDA kernels against the reference-produced fixture."""
+    from tests.mixture_check import run
+    run("cuda")

@@ -207,6 +207,12 @@ def test_family_b_crvae_matches_reference(cpu_backend):
     run("cpu", tol=2e-5)
 
 
+def test_mixture_csrae_matches_reference(cpu_backend):
+    """MixtureCSRAE (CSRAE_new.py) losses and gradients against the reference's own numbers."""
+    from tests.mixture_check import run
+    run("cpu", tol=2e-5)
+
+
 def test_train_phase1_tracks_reference_log(cpu_backend, traj):
     """Host logic of train_phase1 (batch draw, noise-draw order, check block, best-model restore)
     against the reference's golden log, first 101 iterations; generator state ends where the

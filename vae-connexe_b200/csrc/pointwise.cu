@@ -449,6 +449,26 @@ extern "C" int crvae_tanh_bwd(const float* dy, const float* y, float* dx, int64_
 }
 
 namespace crvae {
+// Bernoulli reconstruction loss of MixtureCSRAE (CSRAE_new.py:144): F.binary_cross_entropy_with_logits(reduction="sum"),
+// numerically stable form max(l,0) - l*x + log1p(exp(-|l|)); dlogits = (sigmoid(l) - x) * dscale.  Per-CTA partial sums in
+// fp64, summed in CTA order by bce_finish_kernel (deterministic).
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ x,
+                                                         double* __restrict__ part, float* __restrict__ dlogits, long long n, float dscale) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float l = logits[e], t = x[e];
+        acc += (double)(fmaxf(l, 0.f) - l * t + log1pf(expf(-fabsf(l))));
+        if (dlogits) dlogits[e] = (sigmoidf_acc(l) - t) * dscale;
+    }
+    const double tot = block_sum(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+__global__ void bce_finish_kernel(const double* __restrict__ part, int nparts, float* __restrict__ out) {
+    double s = 0.0;
+    for (int i = 0; i < nparts; ++i) s += part[i];
+    out[0] = (float)s;
+}
 // Family-B ISTA (CRVAE.py:134-150): one warp per row of W_in (one candidate parent), norm over the row's H entries.
 __global__ void ista_rows_kernel(float* __restrict__ w, const float* __restrict__ dw, float* __restrict__ row_norm, long long rows,
                                  int cols, float lr, float thr, int do_prox) {
@@ -502,6 +522,23 @@ __global__ void gen_scatter_kernel(const float* __restrict__ y, const float* __r
 }
 
 }  // namespace crvae
+
+extern "C" size_t crvae_bce_logits_workspace(int64_t n) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    return (size_t)(blocks > 0 ? blocks : 1) * sizeof(double);
+}
+extern "C" int crvae_bce_logits_fwd_bwd(const float* logits, const float* x, float* sum_out, float* dlogits, int64_t n, float dscale,
+                                        void* workspace, void* stream) {
+    CRVAE_REQUIRE(logits && x && sum_out && workspace && n > 0, "bad argument");
+    long long blocks = (n + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    bce_logits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, x, (double*)workspace, dlogits, n, dscale);
+    int rc = check_launch("bce_logits_kernel");
+    if (rc) return rc;
+    bce_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const double*)workspace, (int)blocks, sum_out);
+    return check_launch("bce_finish_kernel");
+}
 
 extern "C" int crvae_ista_rows(float* w, const float* dw, float* row_norm, int64_t rows, int cols, float lr, float thr, int do_prox,
                                void* stream) {

@@ -68,6 +68,8 @@ SIGNATURES = {
     "crvae_dz_allreduce_bytes": (_c_size_t, [_c_int] * 3),
     "crvae_dz_allreduce_latent_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_float, _c_int,
                                               _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "crvae_bce_logits_workspace": (_c_size_t, [_c_i64]),
+    "crvae_bce_logits_fwd_bwd": (_c_int, [_c_void_p] * 4 + [_c_i64, _c_float, _c_void_p, _c_void_p]),
     "crvae_ista_rows": (_c_int, [_c_void_p] * 3 + [_c_i64, _c_int, _c_float, _c_float, _c_int, _c_void_p]),
     "crvae_gen_scatter": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_float, _c_void_p]),
     "crvae_sumsq": (_c_int, [_c_void_p, _c_i64, _c_void_p, _c_void_p]),
@@ -315,6 +317,13 @@ class Kernels:
         arr = (C.c_void_p * world)(*[int(x) for x in peer_ptrs])
         self._ck(self.lib.crvae_dz_allreduce_latent_bwd(ptr(dh0), P, arr, rank, world, ptr(lat), ptr(eps), float(beta), kl_form,
                                                         ptr(dlat), ptr(dz_out), B, Z, stream_ptr()), "crvae_dz_allreduce_latent_bwd")
+
+    def bce_logits_workspace(self, n) -> int:
+        return int(self.lib.crvae_bce_logits_workspace(n))
+
+    def bce_logits_fwd_bwd(self, logits, x, sum_out, dlogits, n, dscale, ws):
+        self._ck(self.lib.crvae_bce_logits_fwd_bwd(ptr(logits), ptr(x), ptr(sum_out), ptr(dlogits), n, float(dscale), ptr(ws),
+                                                   stream_ptr()), "crvae_bce_logits_fwd_bwd")
 
     def ista_rows(self, w, dw, row_norm, rows, cols, lr, thr, do_prox):
         self._ck(self.lib.crvae_ista_rows(ptr(w), ptr(dw), ptr(row_norm), rows, cols, float(lr), float(thr), int(do_prox), stream_ptr()),
