@@ -909,3 +909,10 @@ def test_mixture_csrae_matches_reference():
     space embedded in the 64-dimension divergence kernel) on the CUDA kernels against the reference-produced fixture."""
     from tests.mixture_check import run
     run("cuda")
+
+
+def test_generic_vrae_teacher_forcing_below_one():
+    """VRAE.py with teacher_forcing_ratio < 1 (:85-100, schedules :173-182): the step-by-step decoder with gradient through the
+    fed-back inputs, on the CUDA kernels against the reference-produced fixture."""
+    from tests.vrae_tf_check import run
+    run("cuda")

@@ -213,6 +213,12 @@ def test_mixture_csrae_matches_reference(cpu_backend):
     run("cpu", tol=2e-5)
 
 
+def test_generic_vrae_teacher_forcing_below_one(cpu_backend):
+    """VRAE.py with teacher_forcing_ratio < 1 (:85-100) and its schedules: forward, every gradient and a scheduled Adam run."""
+    from tests.vrae_tf_check import run
+    run("cpu", tol=2e-5)
+
+
 def test_train_phase1_tracks_reference_log(cpu_backend, traj):
     """Host logic of train_phase1 (batch draw, noise-draw order, check block, best-model restore)
     against the reference's golden log, first 101 iterations; generator state ends where the
@@ -423,8 +429,8 @@ def test_generic_vrae_tracks_reference(cpu_backend):
     for k in O.GVRAE_KEYS:
         assert _rel(prm[k], g["final." + k]) < 2e-5, k
     assert np.array_equal(torch.get_rng_state().numpy(), g["rng_after"])
-    with pytest.raises(NotImplementedError):
-        model(data, teacher_forcing_ratio=0.5)
+    r_half, _, _ = model(data, teacher_forcing_ratio=0.5)          # free-running steps: see test_generic_vrae_teacher_forcing_below_one
+    assert r_half.shape == recon.shape and model.engine.free is not None
     s = model.sample(4, 7)
     assert s.shape == (4, 7, 10)
 

@@ -6,8 +6,11 @@ Teacher forcing 1.0 (the reference's default, VRAE.py:134/:157) makes every deco
 (step t reads target[:, t], :82/:97), so the whole decoder is ONE projection GEMM + ONE persistent recurrent
 kernel instead of T GRUCell calls with a host sync each (`torch.rand(1).item()`, :95-96).  The per-step
 `torch.rand(1)` draws are still consumed so the CPU generator stays in lock step with the reference.
-Training with teacher_forcing_ratio < 1 would need the gradient w.r.t. the fed-back inputs, which this path
-does not produce: forward / generate / sample support any ratio, `train` requires 1.0.
+With teacher_forcing_ratio < 1 (VRAE.py:95-100, the schedules of :173-182 used by the reference's own example :196-197) some
+steps feed the model's OWN previous output back: the decoder then runs step by step (projection, one recurrent step, output
+layer per step; the per-step torch.rand(1) decides, as in the reference) and the backward carries the gradient through the
+fed-back inputs (d x_in = d gates . W_ih) -- forward_free / backward_free below.  This path is launch-bound like the
+reference's GRUCell loop; the fused path stays the default (ratio 1.0).
 LSTM / RNN cell types are out of scope.
 """
 from __future__ import annotations
@@ -37,6 +40,7 @@ class _Engine:
         self.grad = self.theta.like()
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.theta.flat), torch.zeros_like(self.theta.flat)
         self.adam_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.adam_counter_st = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.n_trainable = self.theta.offsets["start_token"]      # start_token never gets a gradient under TF = 1
         self.shape = None
 
@@ -72,7 +76,12 @@ class _Engine:
             n = R.dwhh_workspace(k, 1, T, B)
             self.ws_dwhh = torch.zeros(n, dtype=torch.float32, device=dev) if n else None
             self.ws_wgrad = torch.zeros(k.proj_wgrad_workspace(1, T, B, D) // 4 + 4, dtype=torch.float32, device=dev)
+            # free-running (teacher forcing < 1) path: actual decoder inputs, per-step scratch
+            self.dec_xin, self.dxin, self.dh_carry, self.dh_step = z(T, B, D), z(B, D), z(1, B, H), z(1, B, H)
+            self.t_dw_hh, self.t_db_hh, self.t_db_ih = z(1, G, H), z(G), z(G)
+            self.ws_gru1 = torch.zeros(k.gru_bwd_workspace(1, B) // 4 + 4, dtype=torch.float32, device=dev)
         self.xin.copy_(x.transpose(0, 1))
+        self.free = None
 
     def forward(self, eps: torch.Tensor):
         """Teacher-forced forward (VRAE.forward :133-137 with teacher_forcing_ratio = 1)."""
@@ -116,6 +125,11 @@ class _Engine:
                              g["dec_w_hh"].view(1, G, H), g["dec_b_hh"], g["dec_b_ih"], None, None, self.dh0, 1, T, B, self.ws_gru,
                              self.ws_dwhh)
         k.proj_wgrad(self.dec_gates, self.xin, None, g["dec_w_ih"], 1, T, B, D, 0, self.ws_wgrad)
+        self._backward_tail(beta)
+
+    def _backward_tail(self, beta: float):
+        """From dL/dh0 of the decoder back through tanh(fc_z2h z), the reparameterisation + KL, fc_mu / fc_logvar and the encoder."""
+        k, th, g, B, T, D, Z = self.k, self.theta, self.grad, self.B, self.T, self.D, self.Z
         k.tanh_bwd(self.dh0, self.h0, self.dpre0, B * H)
         k.gemm(L.GEMM_TN, 1, H, Z, B, self.dpre0, H, 0, self.zlat, Z, 0, g["z2h_w"], Z, 0)
         k.gemm(L.GEMM_TN, 1, 1, H, B, self.ones_B, 1, 0, self.dpre0, H, 0, g["z2h_b"], H, 0)
@@ -130,9 +144,78 @@ class _Engine:
                              self.ws_dwhh)
         k.proj_wgrad(self.enc_gates, self.xin, None, g["enc_w_ih"], 1, T, B, D, 0, self.ws_wgrad)
 
+    # ------------------------------------------------------------------ teacher forcing < 1 (VRAE.py:68-102)
+    def forward_free(self, eps: torch.Tensor, use_tf, first_from_target: bool):
+        """Decoder step by step: use_tf[t] (t < T-1) = the reference's `torch.rand(1).item() < teacher_forcing_ratio` of step t
+        (:95-96): True -> x_in[t+1] = target[:, t+1], False -> x_in[t+1] = the model's own output of step t (:97-100)."""
+        k, th, B, T, D, Z = self.k, self.theta, self.B, self.T, self.D, self.Z
+        self.eps.copy_(eps.reshape(B, Z), non_blocking=True)
+        k.proj_fwd(self.xin, th["enc_w_ih"], th["enc_b_ih"], self.enc_gates, 1, T, B, D, 0)
+        R.gru_forward_small(k, self.enc_gates, th["enc_b_ih"], th["enc_w_hh"], th["enc_b_hh"], self.h0_zero, 0, None, None,
+                            self.enc_hs, self.enc_ghn, None, 1, T, B, 0)
+        hT = self.enc_hs[0, T - 1]
+        k.gemm(L.GEMM_NT, 1, B, 2 * Z, H, hT, H, 0, th["lat_w"], H, 0, self.lat, 2 * Z, 0, th["lat_b"], 0)
+        k.latent_fwd(self.lat, self.eps, self.zlat, self.kl, B, L.KL_STANDARD, Z)
+        k.gemm(L.GEMM_NT, 1, B, H, Z, self.zlat, Z, 0, th["z2h_w"], Z, 0, self.pre0, H, 0, th["z2h_b"], 0)
+        k.tanh_fwd(self.pre0, self.h0, B * H)
+        if first_from_target:
+            self.dec_xin[0].copy_(self.xin[0])                                             # :80
+        else:
+            self.dec_xin[0].copy_(th["start_token"].expand(B, D))                          # :82
+        for t in range(T):
+            h_prev = self.h0 if t == 0 else self.dec_hs[0, t - 1]
+            k.proj_fwd(self.dec_xin[t:t + 1], th["dec_w_ih"].view(1, G, D), th["dec_b_ih"], self.dec_gates[:, t:t + 1], 1, 1, B, D, 0)
+            R.gru_forward_small(k, self.dec_gates[:, t:t + 1], th["dec_b_ih"], th["dec_w_hh"], th["dec_b_hh"], h_prev, 0, None, None,
+                                self.dec_hs[:, t:t + 1], self.dec_ghn[:, t:t + 1], None, 1, 1, B, 0)   # the GRUCell step, :88
+            k.gemm(L.GEMM_NT, 1, B, D, H, self.dec_hs[0, t], H, 0, th["out_w"], H, 0, self.pre[t], D, 0, th["out_b"], 0)
+            k.act_fwd(self.pre[t], self.recon[t], B * D, self.act)                                     # :91
+            if t < T - 1:
+                self.dec_xin[t + 1].copy_(self.xin[t + 1] if use_tf[t] else self.recon[t])
+        k.mse_fwd_bwd(self.recon, self.xin, self.sse_t, self.drecon, None, T, 1, B * D, 2.0 / B)
+        k.dot_small(self.sse_t, T, 1.0, self.sse)
+        self.free = dict(use_tf=list(use_tf), first_from_target=first_from_target)
+
+    def backward_free(self, beta: float):
+        """Backward of forward_free: BPTT one step at a time, the gradient of a fed-back input (d x_in[t+1] = dgates[t+1] . W_ih)
+        joins d recon[t] wherever step t+1 consumed the model's own output."""
+        k, th, g, B, T, D, Z = self.k, self.theta, self.grad, self.B, self.T, self.D, self.Z
+        use_tf = self.free["use_tf"]
+        g["dec_w_hh"].zero_(); g["dec_b_hh"].zero_(); g["dec_b_ih"].zero_(); g["start_token"].zero_()
+        self.dh_carry.zero_()
+        fed_back = False                                   # does step t+1 read recon[t]?
+        for t in range(T - 1, -1, -1):
+            if fed_back:
+                k.axpy(self.drecon[t], self.dxin, B * D, 1.0)
+            k.act_bwd(self.drecon[t], self.recon[t], self.dpre[t], B * D, self.act)
+            # dh_t = dpre_t . out_w + (carry from step t+1)
+            k.gemm(L.GEMM_NN, 1, B, H, D, self.dpre[t], D, 0, th["out_w"], H, 0, self.dh_step[0], H, 0)
+            k.axpy(self.dh_step, self.dh_carry, B * H, 1.0)
+            h_prev = self.h0 if t == 0 else self.dec_hs[0, t - 1]
+            k.gru_bwd(self.dec_gates[:, t:t + 1], self.dec_ghn[:, t:t + 1], self.dec_hs[:, t:t + 1], h_prev, 0, th["dec_w_hh"], None, None,
+                      self.dh_step, None, self.t_dw_hh, self.t_db_hh, self.t_db_ih, None, None, self.dh_carry, 1, 1, B, self.ws_gru1)
+            k.axpy(g["dec_w_hh"], self.t_dw_hh, G * H, 1.0); k.axpy(g["dec_b_hh"], self.t_db_hh, G, 1.0); k.axpy(g["dec_b_ih"], self.t_db_ih, G, 1.0)
+            fed_back = t > 0 and not use_tf[t - 1]
+            if fed_back or (t == 0 and not self.free["first_from_target"]):
+                k.gemm(L.GEMM_NN, 1, B, D, G, self.dec_gates[0, t], G, 0, th["dec_w_ih"], D, 0, self.dxin, D, 0)   # d x_in[t]
+            if t == 0 and not self.free["first_from_target"]:
+                k.gemm(L.GEMM_TN, 1, 1, D, B, self.ones_B, 1, 0, self.dxin, D, 0, g["start_token"], D, 0)
+        TB = T * B
+        k.gemm(L.GEMM_TN, 1, D, H, TB, self.dpre, D, 0, self.dec_hs, H, 0, g["out_w"], H, 0)
+        k.gemm(L.GEMM_TN, 1, 1, D, TB, self.ones_TB, 1, 0, self.dpre, D, 0, g["out_b"], D, 0)
+        k.proj_wgrad(self.dec_gates, self.dec_xin, None, g["dec_w_ih"], 1, T, B, D, 0, self.ws_wgrad)
+        self.dh0.copy_(self.dh_carry)
+        self._backward_tail(beta)
+
     def adam_step(self, lr: float):
-        self.k.adam_step_dev(self.theta.flat, self.grad.flat, self.exp_avg, self.exp_avg_sq, self.n_trainable,
-                             lr, 0.9, 0.999, 1e-8, self.adam_counter)
+        # start_token has a gradient only when the decoder started from it (teacher_forcing_ratio <= 0); torch.optim.Adam skips
+        # parameters without one
+        # (its own step counter: torch keeps the step count per parameter, and this one starts when its first gradient arrives)
+        n = self.n_trainable
+        self.k.adam_step_dev(self.theta.flat, self.grad.flat, self.exp_avg, self.exp_avg_sq, n, lr, 0.9, 0.999, 1e-8, self.adam_counter)
+        if self.free is not None and not self.free["first_from_target"]:
+            m = self.theta.numel - n
+            self.k.adam_step_dev(self.theta.flat[n:], self.grad.flat[n:], self.exp_avg[n:], self.exp_avg_sq[n:], m, lr, 0.9, 0.999, 1e-8,
+                                 self.adam_counter_st)
 
 
 class VRAE(nn.Module):
@@ -183,14 +266,15 @@ class VRAE(nn.Module):
             torch.rand(1)
 
     def forward(self, x: torch.Tensor, teacher_forcing_ratio: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        if teacher_forcing_ratio < 1.0:
-            raise NotImplementedError("fused path implements teacher_forcing_ratio = 1.0 (the reference default); "
-                                      "use generate()/sample() for free-running decoding")
         e = self.engine
         e.bind(x)
         eps = torch.randn(x.shape[0], self.latent_dim)        # randn_like(std) on the CPU generator (:119)
-        self._consume_tf_draws(x.shape[1])
-        e.forward(eps.to(e.device))
+        if teacher_forcing_ratio >= 1.0:                      # every draw says "teacher forcing": the fused path
+            self._consume_tf_draws(x.shape[1])
+            e.forward(eps.to(e.device))
+        else:                                                 # one torch.rand(1) per non-final step decides (:95-96)
+            use_tf = [torch.rand(1).item() < teacher_forcing_ratio for _ in range(x.shape[1] - 1)]
+            e.forward_free(eps.to(e.device), use_tf, teacher_forcing_ratio > 0)
         Z = self.latent_dim
         return e.recon.permute(1, 0, 2), e.lat[:, :Z], e.lat[:, Z:]
 
@@ -233,14 +317,15 @@ class VRAE(nn.Module):
 
 def train(model: VRAE, data: torch.Tensor, epochs: int = 10, lr: float = 1e-3, beta: float = 1.0,
           teacher_forcing_schedule: Optional[Callable] = None, log: Optional[list] = None) -> None:
-    """train() of VRAE.py (:150-169): full-batch Adam; teacher forcing must stay at 1.0 on this path."""
+    """train() of VRAE.py (:150-169): full-batch Adam, optional teacher-forcing schedule (:173-182)."""
     e = model.engine
     for epoch in range(epochs):
         tf_ratio = teacher_forcing_schedule(epoch) if teacher_forcing_schedule else 1.0
-        if tf_ratio < 1.0:
-            raise NotImplementedError("training with teacher_forcing_ratio < 1 needs input gradients (not on this path)")
         recon, mu, logvar = model(data, teacher_forcing_ratio=tf_ratio)
-        e.backward(beta)
+        if e.free is not None:
+            e.backward_free(beta)
+        else:
+            e.backward(beta)
         e.adam_step(lr)
         if epoch % 10 == 0:
             rec = float(e.sse) / data.shape[0]
