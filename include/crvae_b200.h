@@ -187,6 +187,18 @@ int crvae_gru_bwd_ll(float* gates, float* ghn, const float* hs, const float* h0,
                      const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
                      const float* dhs, float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0,
                      int P, int T, int B, void* workspace, void* stream);
+/* Register-resident tensor-core forms of the two calls above (warp-level mma.sync m16n8k8, 3xTF32; same arguments,
+ * buffers and in-place conventions; results agree with the exact kernels to ~1e-6 relative, like the *_tc kernels).
+ * One CTA per (head, 16-row tile) in a persistent grid; W_hh is held in registers as pre-split tf32 B fragments, the
+ * accumulators land in the registers of the thread that does the gate math, one __syncthreads per step.  The default
+ * recurrent path of every shape (decoder heads, head shards, the encoder, VRAE4E, VRAE.py).                          */
+int crvae_gru_fwd_mma(float* gates, const float* b_ih, const float* w_hh, const float* b_hh,
+                      const float* h0, int64_t h0_head_stride, const float* w_lin, const float* b_lin,
+                      float* hs, float* ghn, float* pred, int P, int T, int B, int t_skip, void* stream);
+int crvae_gru_bwd_mma(float* gates, float* ghn, const float* hs, const float* h0, int64_t h0_head_stride,
+                      const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
+                      const float* dhs, float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0,
+                      int P, int T, int B, void* workspace, void* stream);
 size_t crvae_gru_dwhh_tc_workspace(int P, int T, int B);
 int crvae_gru_dwhh_tc(const float* dgates, const float* dghn, const float* hs, const float* h0,
                       int64_t h0_head_stride, float* dw_hh, int P, int T, int B, void* workspace, void* stream);

@@ -33,6 +33,7 @@ def main():
         res = {}
         res["fwd ffma"] = run(lambda gates: k.gru_fwd(gates, b_ih, w_hh, b_hh, h0, 0, w_lin, b_lin, hs, ghn, pred, P, T, B, 0))
         res["fwd ll"] = run(lambda gates: k.gru_fwd_ll(gates, b_ih, w_hh, b_hh, h0, 0, w_lin, b_lin, hs, ghn, pred, P, T, B, 0))
+        res["fwd mma"] = run(lambda gates: k.gru_fwd_mma(gates, b_ih, w_hh, b_hh, h0, 0, w_lin, b_lin, hs, ghn, pred, P, T, B, 0))
         if T <= 100:
             res["fwd tc"] = run(lambda gates: k.gru_fwd_tc(gates, b_ih, w_hh, None, b_hh, h0, 0, w_lin, b_lin, hs, ghn, pred, P, T, B, 0))
         dpred = torch.randn(P, T, B, device="cuda", generator=g)
@@ -53,6 +54,7 @@ def main():
             return ts[len(ts) // 2]
         res["bwd ffma"] = run_b(lambda gates, gh: k.gru_bwd_deferred(gates, gh, hs, h0, 0, w_hh, w_lin, dpred, None, None, db_hh, db_ih, dw_lin, db_lin, dh0, P, T, B, ws))
         res["bwd ll"] = run_b(lambda gates, gh: k.gru_bwd_ll(gates, gh, hs, h0, 0, w_hh, w_lin, dpred, None, None, db_hh, db_ih, dw_lin, db_lin, dh0, P, T, B, ws))
+        res["bwd mma"] = run_b(lambda gates, gh: k.gru_bwd_mma(gates, gh, hs, h0, 0, w_hh, w_lin, dpred, None, None, db_hh, db_ih, dw_lin, db_lin, dh0, P, T, B, ws))
         if T <= 100:
             res["bwd tc"] = run_b(lambda gates, gh: k.gru_bwd_tc(gates, gh, hs, h0, 0, w_hh, w_lin, dpred, None, db_hh, db_ih, dw_lin, db_lin, dh0, P, T, B, ws))
         print(f"P={P:4d} T={T:4d} B={B:5d}  " + "  ".join(f"{k_} {v:8.1f} us ({v / T:5.2f}/step)" for k_, v in res.items()), flush=True)

@@ -138,7 +138,10 @@ class CRVAEEngine:
         # "ll" = low-latency 16-row tiles (crvae_gru_fwd_ll / _bwd_ll): shards of few heads, where one step's latency is the cost
         import os as _os
         want = _os.environ.get("CRVAE_REC_MODE", "auto")
-        if R.has_ll(self.k) and P > 0 and (want == "ll" or (want == "auto" and P <= R.LL_MAX_HEADS)):
+        # "mma" = register-resident warp-level MMA kernels (crvae_gru_fwd_mma / _bwd_mma, 3xTF32): 16-row tiles, persistent grid
+        if R.has_mma(self.k) and P > 0 and (want == "mma" or (want == "auto" and R.mma_preferred(P))):
+            self.rec_mode = "mma"
+        elif R.has_ll(self.k) and P > 0 and (want == "ll" or (want == "auto" and P <= R.LL_MAX_HEADS)):
             self.rec_mode = "ll"
         elif want in ("auto", "tc3") and hasattr(self.k, "gru_fwd_tc") and P >= 8:
             self.rec_mode = "tc3"
@@ -277,9 +280,10 @@ class CRVAEEngine:
             if self.rec_mode == "tc3":
                 k.gru_fwd_tc(self.gates, th["b_ih"], th["w_hh"], None, th["b_hh"], self.zlat, 0, th["w_lin"],
                              th["b_lin"], self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
-            elif self.rec_mode == "ll":
-                k.gru_fwd_ll(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
-                             self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
+            elif self.rec_mode in ("ll", "mma"):
+                fwd = k.gru_fwd_mma if self.rec_mode == "mma" else k.gru_fwd_ll
+                fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
+                    self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
             else:
                 k.gru_fwd(self.gates, th["b_ih"], th["w_hh"], th["b_hh"], self.zlat, 0, th["w_lin"], th["b_lin"],
                           self.hs, self.ghn, self.pred, P, DEC_STEPS, B, 1)
@@ -350,10 +354,11 @@ class CRVAEEngine:
         # decoder BPTT.  With enough heads the dW_hh accumulation is deferred to one tcgen05 GEMM per head
         # (crvae_gru_dwhh_tc, issued below next to the projection weight gradient); the BPTT itself runs on tcgen05
         # (crvae_gru_bwd_tc) when the rank holds >= 8 heads, else on the exact FFMA2 kernels.
-        defer = (P >= 8 or self.rec_mode == "ll") and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
-        if P > 0 and defer and self.rec_mode == "ll":
-            k.gru_bwd_ll(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
-                         g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
+        defer = (P >= 8 or self.rec_mode in ("ll", "mma")) and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
+        if P > 0 and defer and self.rec_mode in ("ll", "mma"):
+            bwd = k.gru_bwd_mma if self.rec_mode == "mma" else k.gru_bwd_ll
+            bwd(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
+                g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
         elif P > 0 and defer and self.rec_mode == "tc3" and hasattr(k, "gru_bwd_tc"):
             k.gru_bwd_tc(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None,
                          g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
@@ -448,7 +453,7 @@ class CRVAEEngine:
     def flow_supported(self) -> bool:
         k = self.k
         return (self.device.type == "cuda" and self.P > 0 and self.B is not None and self.B % 32 == 0 and not self.packed
-                and self.proj_mode == "tc3" and self.rec_mode in ("tc3", "ll") and self.bwd_mode == "defer"
+                and self.proj_mode == "tc3" and self.rec_mode in ("tc3", "ll", "mma") and self.bwd_mode == "defer"
                 and hasattr(k, "gru_dwhh_tc") and self.ws_lat is not None and self.use_side_stream)
 
     def _flow_setup(self):
@@ -485,8 +490,9 @@ class CRVAEEngine:
             k.gru_fwd_tc(self.gates[sl], th["b_ih"][sl], th["w_hh"][sl], None, th["b_hh"][sl], self.zlat, 0, th["w_lin"][sl],
                          th["b_lin"][sl], self.hs[sl], self.ghn[sl], self.pred[sl], n, DEC_STEPS, B, 1)
         else:
-            k.gru_fwd_ll(self.gates[sl], th["b_ih"][sl], th["w_hh"][sl], th["b_hh"][sl], self.zlat, 0, th["w_lin"][sl], th["b_lin"][sl],
-                         self.hs[sl], self.ghn[sl], self.pred[sl], n, DEC_STEPS, B, 1)
+            fwd = k.gru_fwd_mma if self.rec_mode == "mma" else k.gru_fwd_ll
+            fwd(self.gates[sl], th["b_ih"][sl], th["w_hh"][sl], th["b_hh"][sl], self.zlat, 0, th["w_lin"][sl], th["b_lin"][sl],
+                self.hs[sl], self.ghn[sl], self.pred[sl], n, DEC_STEPS, B, 1)
         k.mse_fwd_bwd(self.pred[sl], self.target[sl], self.sse[sl], self.dpred[sl], None, n, DEC_STEPS, B)
 
     def _flow_bwd_group(self, lo, hi, ws):
@@ -497,8 +503,9 @@ class CRVAEEngine:
             fn(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None,
                g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
         else:
-            k.gru_bwd_ll(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None, None,
-                         g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
+            bwd = k.gru_bwd_mma if self.rec_mode == "mma" else k.gru_bwd_ll
+            bwd(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None, None,
+                g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
 
     def _flow_wgrads_group(self, lo, hi, ws, lam_ridge):
         """dW_hh, dW_ih (+ ridge) of heads [lo, hi)."""

@@ -41,6 +41,8 @@ SIGNATURES = {
     "crvae_gru_bwd_tc": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 9 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
     "crvae_gru_fwd_ll": (_c_int, [_c_void_p] * 5 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
     "crvae_gru_bwd_ll": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 10 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
+    "crvae_gru_fwd_mma": (_c_int, [_c_void_p] * 5 + [_c_i64] + [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
+    "crvae_gru_bwd_mma": (_c_int, [_c_void_p] * 4 + [_c_i64] + [_c_void_p] * 10 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
     "crvae_gru_dwhh_tc_workspace": (_c_size_t, [_c_int] * 3),
     "crvae_gru_dwhh_tc": (_c_int, [_c_void_p] * 4 + [_c_i64, _c_void_p] + [_c_int] * 3 + [_c_void_p, _c_void_p]),
     "crvae_latent_fwd": (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _c_int, _c_void_p]),
@@ -227,6 +229,17 @@ class Kernels:
         self._ck(self.lib.crvae_gru_bwd_ll(ptr(gates), ptr(ghn), ptr(hs), ptr(h0), h0_stride, ptr(w_hh), ptr(w_lin),
                                            ptr(dpred), ptr(dh_last), ptr(dhs), ptr(db_hh), ptr(db_ih), ptr(dw_lin),
                                            ptr(db_lin), ptr(dh0), P, T, B, ptr(ws), stream_ptr()), "crvae_gru_bwd_ll")
+
+    def gru_fwd_mma(self, gates, b_ih, w_hh, b_hh, h0, h0_stride, w_lin, b_lin, hs, ghn, pred, P, T, B, t_skip):
+        self._ck(self.lib.crvae_gru_fwd_mma(ptr(gates), ptr(b_ih), ptr(w_hh), ptr(b_hh), ptr(h0), h0_stride, ptr(w_lin),
+                                            ptr(b_lin), ptr(hs), ptr(ghn), ptr(pred), P, T, B, t_skip, stream_ptr()),
+                 "crvae_gru_fwd_mma")
+
+    def gru_bwd_mma(self, gates, ghn, hs, h0, h0_stride, w_hh, w_lin, dpred, dh_last, dhs, db_hh, db_ih, dw_lin, db_lin,
+                    dh0, P, T, B, ws):
+        self._ck(self.lib.crvae_gru_bwd_mma(ptr(gates), ptr(ghn), ptr(hs), ptr(h0), h0_stride, ptr(w_hh), ptr(w_lin),
+                                            ptr(dpred), ptr(dh_last), ptr(dhs), ptr(db_hh), ptr(db_ih), ptr(dw_lin),
+                                            ptr(db_lin), ptr(dh0), P, T, B, ptr(ws), stream_ptr()), "crvae_gru_bwd_mma")
 
     def gru_dwhh_tc_workspace(self, P, T, B) -> int:
         return int(self.lib.crvae_gru_dwhh_tc_workspace(P, T, B))
