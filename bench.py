@@ -192,9 +192,11 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 STAGE_FNS = ["proj_fwd", "proj_fwd_tc", "split_tf32", "split_tf32_gate_rows", "proj_wgrad_tc", "gru_fwd_tc", "gru_bwd_deferred", "gru_bwd_tc",
              "gru_dwhh_tc", "gru_fwd", "gemm", "latent_fwd", "latent_head_fwd", "latent_head_bwd", "mse_fwd_bwd", "dot_small", "gru_bwd",
-             "proj_wgrad", "latent_bwd", "gd_prox_gc", "gd_step", "axpy", "gru_fwd_ll", "gru_bwd_ll", "dz_allreduce", "enc_chain_fwd"]
+             "proj_wgrad", "latent_bwd", "gd_prox_gc", "gd_step", "axpy", "gru_fwd_ll", "gru_bwd_ll", "gru_fwd_mma", "gru_bwd_mma",
+             "dz_allreduce", "enc_chain_fwd"]
 P_ARG = {"proj_fwd": 4, "gru_fwd": 11, "gru_bwd": 16, "proj_wgrad": 4, "proj_fwd_tc": 6, "proj_wgrad_tc": 5, "gru_fwd_tc": 12,
-         "gru_bwd_deferred": 15, "gru_bwd_tc": 14, "gru_dwhh_tc": 6, "gru_fwd_ll": 11, "gru_bwd_ll": 15}
+         "gru_bwd_deferred": 15, "gru_bwd_tc": 14, "gru_dwhh_tc": 6, "gru_fwd_ll": 11, "gru_bwd_ll": 15,
+         "gru_fwd_mma": 11, "gru_bwd_mma": 15}
 
 
 def profile_stages(run, eps_list, reps):
@@ -500,9 +502,9 @@ def run_ours(args):
         tf32_src = "measured here (cuBLAS TF32 8192^3, burst)" if "tf32_tflops" in pk else "bf16 burst / 2 (not measured: --lean)"
         # algorithmic HBM bytes / flops per launch (DESIGN.md "Kernels")
         alg = {}
-        for nm in ("gru_bwd", "gru_bwd_deferred", "gru_bwd_tc", "gru_bwd_ll"):
+        for nm in ("gru_bwd", "gru_bwd_deferred", "gru_bwd_tc", "gru_bwd_ll", "gru_bwd_mma"):
             alg[nm + "[dec]"] = ("hbm", 1796.0 * units_loc)
-        for nm in ("gru_fwd", "gru_fwd_tc", "gru_fwd_ll"):
+        for nm in ("gru_fwd", "gru_fwd_tc", "gru_fwd_ll", "gru_fwd_mma"):
             alg[nm + "[dec]"] = ("hbm", 1028.0 * units_loc)
         for nm in ("proj_fwd", "proj_wgrad", "proj_fwd_tc", "proj_wgrad_tc"):
             alg[nm + "[dec]"] = ("tensor", 2.0 * K * G * 0.9 * units_loc)

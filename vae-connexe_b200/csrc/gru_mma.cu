@@ -707,7 +707,7 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
                 wl[0] = w2.x; wl[1] = w2.y;
                 blin = __ldg(a.b_lin + head);
             }
-            if (ptid < MG) sm.bih[head & 1][ptid] = __ldg(a.b_ih + (long long)head * MG + ptid);      // read after the next P-warp barrier
+            if (ptid < MG) sm.bih[head & 1][ptid] = __ldg(a.b_ih + (long long)head * MG + ptid);      // read after a P-warp barrier
             cur_head = head;
         };
         auto load_h0 = [&](float2 (&h)[2], const FwdPos& p) {
@@ -791,7 +791,10 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
                 h0n[0] = h0n[1] = make_float2(0.f, 0.f);
                 if (last_step && next_active) load_h0(h0n, nx);
                 if (pp.vrows > 0) {
-                    if (pp.head != cur_head) load_head(pp.head);
+                    if (pp.head != cur_head) {    // (uniform across the P warps) new head: biases, and its b_ih copy before anyone reads it
+                        load_head(pp.head);
+                        p_warps_sync();
+                    }
                     const long long pc0 = MMA_CLK();
                     mbar_wait(&st.slab_full[n % PF_NS], (uint32_t)(n / PF_NS) & 1u);
                     const long long pc1 = MMA_CLK();
