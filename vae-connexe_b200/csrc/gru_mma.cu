@@ -894,6 +894,359 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Warp-specialised BPTT (dW_hh deferred): the mirror image of gru_fwd_mma_ws_kernel.
+//   * warps 0-7, "M": hold W_hh [192 x 64] as B fragments (n-tile = the warp's 8 hidden units, 24 k-steps), wait for a
+//     tile's gate-gradient operand dgh = [da_r | da_z | da_n*r] (16 x 192, fragment order), issue its 72 MMAs
+//     (3xTF32, one accumulator per term) and hand dgh . W_hh to their partner warp through shared memory;
+//   * warps 8-15, "P": cell backward at 4 elements per thread (dh_t = dh_{t+1}*z + dgh.W_hh arrives from M), staging of
+//     dgi (in place over r|z|n), dgh_n (in place over gh_n) and of the next operand, the column sums
+//     (db_ih, db_hh, dw_lin, db_lin: 11 register accumulators per tile, reduced in fixed order), TMA plumbing.
+// Per step a stream's inputs -- r|z|n (12 KB), gh_n, h_{t-1} (and dhs) tiles -- arrive by TMA into a 3-deep ring on one
+// mbarrier; dgi / dgh_n leave by TMA.  Two tiles of one head per CTA (streams a, b) once there are more tiles than SMs.
+// ------------------------------------------------------------------------------------------------------------
+struct __align__(1024) BwdStreamSmem {
+    float slab[PF_NS][M_ROWS * MG];        // r|z|n -> dgi                      [row][6 x 128 B] swizzled
+    float gn[PF_NS][M_ROWS * MH];          // gh_n -> dgh_n                     [row][2 x 128 B] swizzled
+    float hp[PF_NS][M_ROWS * MH];          // h_{t-1}
+    float de[PF_NS][M_ROWS * MH];          // dhs (per-step gradient into h_t), when present
+    float dgh[2][M_ROWS * MG];             // the A operand of the step, fragment order (frag_idx), by step parity
+    float accb[8][32 * 4];                 // dgh . W_hh of the warp's units, [M warp][lane] x float4 (C-fragment order)
+    uint64_t in_full[PF_NS];
+    uint64_t dgh_ready;
+    uint64_t acc_ready[8];
+};
+struct __align__(1024) BwdPipeSmem { BwdStreamSmem st[2]; };
+
+struct BwdTmaps { CUtensorMap g, n, h, z, d; };
+
+template <bool HAS_DHS>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int pf, int npph, int h0_per_head) {
+    using namespace umma;
+    extern __shared__ __align__(1024) uint8_t mma_smem_raw[];
+    BwdPipeSmem& sm = *reinterpret_cast<BwdPipeSmem*>(mma_smem_raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int w = warp & 7;
+    const bool is_m = warp < 8;
+    const int total = a.P * npph;
+    const int first = (int)((long long)blockIdx.x * total / gridDim.x);
+    const int last = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+    if (first >= last) return;
+    const int ucol = 8 * w + 2 * q;
+    const bool has_lin = a.w_lin != nullptr;
+    const int T = a.T, B = a.B;
+    const int nsteps = (last - first) * T;
+    constexpr uint32_t IN_BYTES = (uint32_t)(M_ROWS * (MG + 2 * MH + (HAS_DHS ? MH : 0)) * 4);
+
+    // step n of stream s: pair j = n / T, time t = T - 1 - n % T (the BPTT walks backwards)
+    auto pos_of_pair = [&](int j, int s) {
+        FwdPos p;
+        p.j = j; p.t = T - 1;
+        const int pj = first + j;
+        p.head = pj / npph;
+        p.tile = (pj - p.head * npph) * pf + s;
+        const int b0 = p.tile * M_ROWS;
+        p.vrows = (pj < last && s < pf && b0 < B) ? min(M_ROWS, B - b0) : 0;
+        return p;
+    };
+    auto advance = [&](FwdPos& p, int s) {
+        if (--p.t < 0) p = pos_of_pair(p.j + 1, s);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+            for (int i = 0; i < PF_NS; ++i) mbar_init(&sm.st[s].in_full[i], 1);
+            mbar_init(&sm.st[s].dgh_ready, 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mbar_init(&sm.st[s].acc_ready[i], 1);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (is_m) {
+        // =============================================================== M warps ===============================================================
+        uint32_t bhi[24][2], blo[24][2];
+        int cur_head = -1;
+        auto load_head = [&](int head) {          // B[k][n] = W_hh[k][8w + n]; k-step ks, k-slots q / q+4 <-> k = 2p, 2p+1, p = 8*(ks/2) + 2q + ks%2
+            const float* __restrict__ W = a.w_hh + (long long)head * MG * MH + 8 * w + g;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                const float* p = W + (long long)(16 * c + 4 * q) * MH;
+                const float v0 = __ldg(p), v1 = __ldg(p + MH), v2 = __ldg(p + 2 * MH), v3 = __ldg(p + 3 * MH);
+                split_tf32_fast(v0, bhi[2 * c][0], blo[2 * c][0]);
+                split_tf32_fast(v1, bhi[2 * c][1], blo[2 * c][1]);
+                split_tf32_fast(v2, bhi[2 * c + 1][0], blo[2 * c + 1][0]);
+                split_tf32_fast(v3, bhi[2 * c + 1][1], blo[2 * c + 1][1]);
+            }
+            cur_head = head;
+        };
+        FwdPos pos[2] = {pos_of_pair(0, 0), pos_of_pair(0, 1)};
+        uint32_t cnt[2] = {0, 0};
+        for (int n = 0; n < nsteps; ++n) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (pos[s].vrows > 0) {
+                    if (pos[s].head != cur_head) load_head(pos[s].head);
+                    BwdStreamSmem& st = sm.st[s];
+                    mbar_wait(&st.dgh_ready, cnt[s] & 1u);
+                    const float* db = st.dgh[cnt[s] & 1];
+                    float acc[3][4];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[k][e] = 0.f;
+#pragma unroll
+                    for (int grp = 0; grp < 6; ++grp) {
+                        float4 av[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int ks = 4 * grp + k;
+                            av[k] = *reinterpret_cast<const float4*>(&db[frag_idx(8 * (ks >> 1) + 2 * q + (ks & 1), g)]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int ks = 4 * grp + k;
+                            uint32_t ahi[4], alo[4];
+                            split_tf32_fast(av[k].x, ahi[0], alo[0]); split_tf32_fast(av[k].y, ahi[1], alo[1]);
+                            split_tf32_fast(av[k].z, ahi[2], alo[2]); split_tf32_fast(av[k].w, ahi[3], alo[3]);
+                            mma_tf32(acc[0], alo, bhi[ks]);
+                            mma_tf32(acc[1], ahi, blo[ks]);
+                            mma_tf32(acc[2], ahi, bhi[ks]);
+                        }
+                    }
+                    float4 o;
+                    o.x = __fadd_rn(__fadd_rn(acc[0][0], acc[1][0]), acc[2][0]); o.y = __fadd_rn(__fadd_rn(acc[0][1], acc[1][1]), acc[2][1]);
+                    o.z = __fadd_rn(__fadd_rn(acc[0][2], acc[1][2]), acc[2][2]); o.w = __fadd_rn(__fadd_rn(acc[0][3], acc[1][3]), acc[2][3]);
+                    *reinterpret_cast<float4*>(&st.accb[w][lane * 4]) = o;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&st.acc_ready[w]);
+                    ++cnt[s];
+                }
+                advance(pos[s], s);
+            }
+        }
+    } else {
+        // =============================================================== P warps ===============================================================
+        const int ptid = tid - 256;
+        float wl[2] = {0.f, 0.f};
+        int cur_head = -1;
+        auto load_head = [&](int head) {
+            if (has_lin) {
+                const float2 w2 = __ldg(reinterpret_cast<const float2*>(a.w_lin + (long long)head * MH + ucol));
+                wl[0] = w2.x; wl[1] = w2.y;
+            }
+            cur_head = head;
+        };
+        // ---- plumbing (thread 256) ----
+        auto issue_load = [&](int s, int n) {         // inputs of step n -> ring slot n % NS
+            const int j = n / T;
+            FwdPos p = pos_of_pair(j, s);
+            p.t = T - 1 - (n - j * T);
+            const int slot = n % PF_NS;
+            BwdStreamSmem& st = sm.st[s];
+            mbar_arrive_expect_tx(&st.in_full[slot], p.vrows > 0 ? IN_BYTES : 0u);
+            if (p.vrows > 0) {
+                const int c2 = p.tile * M_ROWS, c3 = p.head * T + p.t;
+                tma_load_4d(st.slab[slot], &tm.g, &st.in_full[slot], 0, 0, c2, c3);
+                tma_load_4d(st.gn[slot], &tm.n, &st.in_full[slot], 0, 0, c2, c3);
+                if (p.t > 0) tma_load_4d(st.hp[slot], &tm.h, &st.in_full[slot], 0, 0, c2, c3 - 1);
+                else         tma_load_4d(st.hp[slot], &tm.z, &st.in_full[slot], 0, 0, c2, h0_per_head ? p.head : 0);
+                if (HAS_DHS) tma_load_4d(st.de[slot], &tm.d, &st.in_full[slot], 0, 0, c2, c3);
+            }
+        };
+        auto plumb = [&](int s, int n, const FwdPos& p) {    // all P warps have staged step n of stream s
+            if (pf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (p.vrows > 0) {
+                const int c2 = p.tile * M_ROWS, c3 = p.head * T + p.t;
+                tma_store_4d(&tm.g, sm.st[s].slab[n % PF_NS], 0, 0, c2, c3);
+                tma_store_4d(&tm.n, sm.st[s].gn[n % PF_NS], 0, 0, c2, c3);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (n >= 1 && n - 1 + PF_NS < nsteps) issue_load(s, n - 1 + PF_NS);
+        };
+        auto load_dp = [&](float (&dp)[2], const FwdPos& p) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = g + 8 * i;
+                dp[i] = (has_lin && r < p.vrows) ? __ldg(a.dpred + ((long long)p.head * T + p.t) * B + p.tile * M_ROWS + r) : 0.f;
+            }
+        };
+        auto load_tile_start = [&](float2 (&dhl)[2], float2 (&hl)[2], const FwdPos& p) {     // dh_last and h_{T-1} of a tile
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = g + 8 * i, b = p.tile * M_ROWS + r;
+                dhl[i] = make_float2(0.f, 0.f); hl[i] = make_float2(0.f, 0.f);
+                if (r < p.vrows) {
+                    if (a.dh_last) dhl[i] = __ldg(reinterpret_cast<const float2*>(a.dh_last + ((long long)p.head * B + b) * MH + ucol));
+                    if (has_lin) hl[i] = __ldg(reinterpret_cast<const float2*>(a.hs + (((long long)p.head * T + (T - 1)) * B + b) * MH + ucol));
+                }
+            }
+        };
+
+        int o_r[2], o_z[2], o_n[2], o_h[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            o_r[i] = sw_idx(6, g + 8 * i, ucol); o_z[i] = sw_idx(6, g + 8 * i, MH + ucol); o_n[i] = sw_idx(6, g + 8 * i, 2 * MH + ucol);
+            o_h[i] = sw_idx(2, g + 8 * i, ucol);
+        }
+        const int o_frag = frag_idx(4 * w + q, g);
+        FwdPos pos[2] = {pos_of_pair(0, 0), pos_of_pair(0, 1)};
+        // per-stream state
+        float dh[2][2][2], dhz[2][2][2];          // [stream][row][unit]
+        float2 hcur[2][2];                        // h_t of the step being processed (dw_lin += dpred[t] * h_t)
+        float dpn[2][2];                          // dpred of the stream's next step (prefetched)
+        float2 dhl[2][2], hl[2][2];               // next tile's dh_last / h_{T-1} (prefetched during the last step of a tile)
+        float sums[2][11];                        // db_ih r,z,n (x2 units) | db_hh n (x2) | dw_lin (x2) | db_lin
+        bool pending[2] = {false, false};         // an MMA result of this stream is outstanding
+        FwdPos ppos[2] = {pos[0], pos[1]};        // position of the outstanding step
+        uint32_t cnt[2] = {0, 0}, dcnt[2] = {0, 0};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            load_dp(dpn[s], pos[s]);
+            load_tile_start(dhl[s], hl[s], pos[s]);
+#pragma unroll
+            for (int k = 0; k < 11; ++k) sums[s][k] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { dh[s][i][0] = dh[s][i][1] = 0.f; dhz[s][i][0] = dhz[s][i][1] = 0.f; hcur[s][i] = make_float2(0.f, 0.f); }
+        }
+        load_head(pos[0].head);
+        if (ptid == 0) {
+            for (int n = 0; n < PF_NS && n < nsteps; ++n) { issue_load(0, n); if (pf == 2) issue_load(1, n); }
+        }
+        // finish the outstanding step of stream s: dh_{t-1} = dh_t * z + dgh . W_hh; at a tile end write dh0 and the tile's column sums
+        auto finish = [&](int s) {
+            BwdStreamSmem& st = sm.st[s];
+            mbar_wait(&st.acc_ready[w], cnt[s] & 1u);
+            ++cnt[s];
+            const float4 v = *reinterpret_cast<const float4*>(&st.accb[w][lane * 4]);
+            dh[s][0][0] = __fadd_rn(dhz[s][0][0], v.x); dh[s][0][1] = __fadd_rn(dhz[s][0][1], v.y);
+            dh[s][1][0] = __fadd_rn(dhz[s][1][0], v.z); dh[s][1][1] = __fadd_rn(dhz[s][1][1], v.w);
+            pending[s] = false;
+            const FwdPos& p = ppos[s];
+            if (p.t == 0) {                       // tile end
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = g + 8 * i;
+                    if (r < p.vrows) stg2(a.dh0 + ((long long)p.head * B + p.tile * M_ROWS + r) * MH + ucol, dh[s][i][0], dh[s][i][1]);
+                }
+                float vv[11];
+#pragma unroll
+                for (int k = 0; k < 11; ++k) {
+                    vv[k] = sums[s][k];
+                    vv[k] += __shfl_xor_sync(0xffffffffu, vv[k], 4);
+                    vv[k] += __shfl_xor_sync(0xffffffffu, vv[k], 8);
+                    vv[k] += __shfl_xor_sync(0xffffffffu, vv[k], 16);
+                    sums[s][k] = 0.f;
+                }
+                if (g == 0) {
+                    float* ws = a.ws + ((long long)p.head * a.ntiles + p.tile) * MWS_TILE;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int u = ucol + e;
+                        ws[MWS_DBIH + u] = vv[e];            ws[MWS_DBHH + u] = vv[e];                  // r: dgh == dgi
+                        ws[MWS_DBIH + MH + u] = vv[2 + e];   ws[MWS_DBHH + MH + u] = vv[2 + e];         // z
+                        ws[MWS_DBIH + 2 * MH + u] = vv[4 + e];                                          // n: db_ih
+                        ws[MWS_DBHH + 2 * MH + u] = vv[6 + e];                                          // n: db_hh (dgh_n)
+                        ws[MWS_DWLIN + u] = vv[8 + e];
+                    }
+                    if (w == 0 && q == 0) ws[MWS_DBLIN] = vv[10];
+                }
+            }
+        };
+
+        for (int n = 0; n < nsteps; ++n) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s == 1 && pf == 1) break;
+                BwdStreamSmem& st = sm.st[s];
+                const FwdPos pp = pos[s];
+                FwdPos nx = pp;
+                advance(nx, s);
+                if (pending[s]) finish(s);
+                if (pp.vrows > 0) {
+                    if (pp.head != cur_head) load_head(pp.head);
+                    if (pp.t == T - 1) {          // tile start
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) { dh[s][i][0] = dhl[s][i].x; dh[s][i][1] = dhl[s][i].y; hcur[s][i] = hl[s][i]; }
+                    }
+                    const float dp[2] = {dpn[s][0], dpn[s][1]};
+                    // prefetch for the stream's next step
+                    if (nx.vrows > 0) {
+                        load_dp(dpn[s], nx);
+                        if (nx.t == T - 1) load_tile_start(dhl[s], hl[s], nx);
+                    }
+                    const int slot = n % PF_NS;
+                    mbar_wait(&st.in_full[slot], (uint32_t)(n / PF_NS) & 1u);
+                    float* slab = st.slab[slot];
+                    float* gns = st.gn[slot];
+                    const float* hps = st.hp[slot];
+                    float fr[4], fz[4], fn_[4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float2 r2 = *reinterpret_cast<const float2*>(slab + o_r[i]), z2 = *reinterpret_cast<const float2*>(slab + o_z[i]),
+                                     n2 = *reinterpret_cast<const float2*>(slab + o_n[i]);
+                        const float2 g2 = *reinterpret_cast<const float2*>(gns + o_h[i]);
+                        const float2 p2 = *reinterpret_cast<const float2*>(hps + o_h[i]);
+                        float2 e2 = make_float2(0.f, 0.f);
+                        if (HAS_DHS) e2 = *reinterpret_cast<const float2*>(st.de[slot] + o_h[i]);
+                        const float r_[2] = {r2.x, r2.y}, z_[2] = {z2.x, z2.y}, n_[2] = {n2.x, n2.y}, gn_[2] = {g2.x, g2.y}, hp_[2] = {p2.x, p2.y},
+                                    de_[2] = {e2.x, e2.y};
+                        const float hc_[2] = {hcur[s][i].x, hcur[s][i].y};
+                        float dar[2], daz[2], dan[2], dgn[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float d = dh[s][i][e] + dp[i] * wl[e] + de_[e];      // total dL/dh_t (same order as gru_bwd_kernel)
+                            const float dn = d * (1.f - z_[e]);
+                            const float dz = d * (hp_[e] - n_[e]);
+                            dan[e] = dn * (1.f - n_[e] * n_[e]);
+                            const float dr = dan[e] * gn_[e];
+                            dar[e] = dr * r_[e] * (1.f - r_[e]);
+                            daz[e] = dz * z_[e] * (1.f - z_[e]);
+                            dgn[e] = dan[e] * r_[e];
+                            dhz[s][i][e] = d * z_[e];
+                            sums[s][e] += dar[e]; sums[s][2 + e] += daz[e]; sums[s][4 + e] += dan[e]; sums[s][6 + e] += dgn[e];
+                            sums[s][8 + e] = fmaf(dp[i], hc_[e], sums[s][8 + e]);
+                        }
+                        if (w == 0 && q == 0) sums[s][10] += dp[i];
+                        hcur[s][i] = p2;
+                        *reinterpret_cast<float2*>(slab + o_r[i]) = make_float2(dar[0], dar[1]);
+                        *reinterpret_cast<float2*>(slab + o_z[i]) = make_float2(daz[0], daz[1]);
+                        *reinterpret_cast<float2*>(slab + o_n[i]) = make_float2(dan[0], dan[1]);
+                        *reinterpret_cast<float2*>(gns + o_h[i]) = make_float2(dgn[0], dgn[1]);
+                        fr[i] = dar[0]; fr[2 + i] = dar[1];
+                        fz[i] = daz[0]; fz[2 + i] = daz[1];
+                        fn_[i] = dgn[0]; fn_[2 + i] = dgn[1];
+                    }
+                    float* db = st.dgh[dcnt[s] & 1];
+                    ++dcnt[s];
+                    *reinterpret_cast<float4*>(db + o_frag) = make_float4(fr[0], fr[1], fr[2], fr[3]);
+                    *reinterpret_cast<float4*>(db + o_frag + 32 * 32) = make_float4(fz[0], fz[1], fz[2], fz[3]);            // frag_idx(32 + p, g) = frag_idx(p, g) + 32*8*4
+                    *reinterpret_cast<float4*>(db + o_frag + 64 * 32) = make_float4(fn_[0], fn_[1], fn_[2], fn_[3]);
+                    fence_proxy_async_smem();
+                    pending[s] = true;
+                    ppos[s] = pp;
+                }
+                p_warps_sync();
+                if (ptid == 0) {
+                    if (pp.vrows > 0) mbar_arrive(&st.dgh_ready);
+                    plumb(s, n, pp);
+                }
+                pos[s] = nx;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (pending[s]) finish(s);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 static int mma_num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -986,9 +1339,43 @@ extern "C" int crvae_gru_bwd_mma(float* gates, float* ghn, const float* hs, cons
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)P * ntiles;
     const int grid = (int)(total < mma_num_sms() ? total : mma_num_sms());
-    if (dhs) gru_bwd_mma_kernel<true><<<grid, M_THREADS, 0, st>>>(a);
-    else     gru_bwd_mma_kernel<false><<<grid, M_THREADS, 0, st>>>(a);
-    int rc = check_launch("gru_bwd_mma_kernel");
+    static const int variant = [] { const char* e = getenv("CRVAE_MMA_BWD_VARIANT"); return e ? atoi(e) : 1; }();
+    int rc;
+    if (variant == 0) {
+        if (dhs) gru_bwd_mma_kernel<true><<<grid, M_THREADS, 0, st>>>(a);
+        else     gru_bwd_mma_kernel<false><<<grid, M_THREADS, 0, st>>>(a);
+        rc = check_launch("gru_bwd_mma_kernel");
+    } else {
+        const int pf = total > mma_num_sms() ? 2 : 1;
+        const int npph = (ntiles + pf - 1) / pf;
+        const long long units = (long long)P * npph;
+        const int wgrid = (int)(units < mma_num_sms() ? units : mma_num_sms());
+        BwdTmaps tm;
+        const uint64_t PT = (uint64_t)P * T;
+        const uint64_t dg[4] = {32, 6, (uint64_t)B, PT}, sg[3] = {128, (uint64_t)MG * 4, (uint64_t)B * MG * 4};
+        const uint32_t bg[4] = {32, 6, M_ROWS, 1};
+        if ((rc = make_tmap_generic(&tm.g, gates, 4, dg, sg, bg, false))) return rc;
+        const uint64_t dh[4] = {32, 2, (uint64_t)B, PT}, sh[3] = {128, (uint64_t)MH * 4, (uint64_t)B * MH * 4};
+        const uint32_t bh[4] = {32, 2, M_ROWS, 1};
+        if ((rc = make_tmap_generic(&tm.n, ghn, 4, dh, sh, bh, false))) return rc;
+        if ((rc = make_tmap_generic(&tm.h, hs, 4, dh, sh, bh, false))) return rc;
+        if ((rc = make_tmap_generic(&tm.d, dhs ? dhs : hs, 4, dh, sh, bh, false))) return rc;
+        const int per_head = h0_head_stride != 0;
+        const uint64_t dz[4] = {32, 2, (uint64_t)B, (uint64_t)(per_head ? P : 1)};
+        const uint64_t sz[3] = {128, (uint64_t)MH * 4, (uint64_t)(per_head ? h0_head_stride : (int64_t)B * MH) * 4};
+        if ((rc = make_tmap_generic(&tm.z, h0, 4, dz, sz, bh, false))) return rc;
+        const int smem = (int)sizeof(BwdPipeSmem);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e1 = cudaFuncSetAttribute(gru_bwd_mma_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaError_t e2 = cudaFuncSetAttribute(gru_bwd_mma_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("gru_bwd_mma_ws smem attr (%d B): %s", smem, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return (int)(e1 != cudaSuccess ? e1 : e2); }
+            attr_done = true;
+        }
+        if (dhs) gru_bwd_mma_ws_kernel<true><<<wgrid, WS_THREADS, smem, st>>>(tm, a, pf, npph, per_head);
+        else     gru_bwd_mma_ws_kernel<false><<<wgrid, WS_THREADS, smem, st>>>(tm, a, pf, npph, per_head);
+        rc = check_launch("gru_bwd_mma_ws_kernel");
+    }
     if (rc) return rc;
     return launch_gru_bwd_finalize((const float*)workspace, db_hh, db_ih, dw_lin, db_lin, P, ntiles, st);
 }

@@ -356,7 +356,7 @@ class CRVAEEngine:
         # (crvae_gru_bwd_tc) when the rank holds >= 8 heads, else on the exact FFMA2 kernels.
         defer = (P >= 8 or self.rec_mode in ("ll", "mma")) and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
         if P > 0 and defer and self.rec_mode in ("ll", "mma"):
-            bwd = k.gru_bwd_mma if self.rec_mode == "mma" else k.gru_bwd_ll
+            bwd = k.gru_bwd_mma if (self.rec_mode == "mma" and R.mma_bwd_preferred(k, P, B)) else k.gru_bwd_ll
             bwd(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
                 g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
         elif P > 0 and defer and self.rec_mode == "tc3" and hasattr(k, "gru_bwd_tc"):
@@ -503,7 +503,7 @@ class CRVAEEngine:
             fn(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None,
                g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
         else:
-            bwd = k.gru_bwd_mma if self.rec_mode == "mma" else k.gru_bwd_ll
+            bwd = k.gru_bwd_mma if (self.rec_mode == "mma" and R.mma_bwd_preferred(k, n, B)) else k.gru_bwd_ll
             bwd(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None, None,
                 g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
 
@@ -549,13 +549,27 @@ class CRVAEEngine:
         k, th, g, B, P, p_ = self.k, self.theta, self.grad, self.B, self.P, self.p
         self._dz_latent_bwd(beta)
         k.latent_head_bwd(self.dlat, self.enc_hs[0, ENC_STEPS - 1], th["lat_w"], g["lat_w"], g["lat_b"], self.dhT, B)
-        R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
-                             None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
-                             1, ENC_STEPS, B, self.ws_gru_enc, self.ws_dwhh_enc)
+        dwhh = R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
+                                    None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
+                                    1, ENC_STEPS, B, self.ws_gru_enc, self.ws_dwhh_enc, split_dwhh=self.device.type == "cuda" and self.use_side_stream)
+        # the two encoder weight-gradient GEMMs only read the BPTT's outputs: side by side on two streams (this chain is the
+        # critical path of a head-sharded iteration)
+        ev_aux = None
+        if dwhh is not None:
+            cur = torch.cuda.current_stream()
+            if getattr(self, "_aux", None) is None:
+                self._aux = torch.cuda.Stream(device=self.device, priority=-1)
+            ev = torch.cuda.Event(); ev.record(cur)
+            self._aux.wait_event(ev)
+            with torch.cuda.stream(self._aux):
+                dwhh()
+                ev_aux = torch.cuda.Event(); ev_aux.record(self._aux)
         if self.enc_tc and self.ws_wgrad_tc_enc is not None:
             k.proj_wgrad_tc(self.enc_gates, self.enc_in_hi, self.enc_in_lo, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad_tc_enc)
         else:
             k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
+        if ev_aux is not None:
+            torch.cuda.current_stream().wait_event(ev_aux)
 
     def flow_pre(self):
         """pre: encoder chain on the staged noise (eps_next) + every head's projection, for the CURRENT weights."""

@@ -35,6 +35,16 @@ def mma_preferred(P: int) -> bool:
     return MMA_MODE == "1" or (MMA_MODE == "small" and P <= MMA_MAX_HEADS)
 
 
+# BPTT: the warp-specialised MMA kernel wins up to ~320 16-row tiles (B = 256, T = 10, us: P = 1: ll 42.1, mma 37.9; P = 13: ll 66.4,
+# mma 56.1; P = 25: ll 91.1, mma 99.3; P = 50: ll 163, mma 142, tcgen05 110), the exact low-latency kernel between that and the
+# tcgen05 range
+MMA_BWD_MAX_TILES = int(os.environ.get("CRVAE_MMA_BWD_MAX_TILES", "320"))
+
+
+def mma_bwd_preferred(k, P: int, B: int) -> bool:
+    return has_mma(k) and (MMA_MODE == "1" or not has_ll(k) or P * ((B + 15) // 16) <= MMA_BWD_MAX_TILES)
+
+
 def has_ll(k) -> bool:
     return LL_ENABLED and hasattr(k, "gru_fwd_ll") and hasattr(k, "gru_bwd_ll")
 
@@ -53,11 +63,17 @@ def dwhh_workspace(k, P, T, B):
 
 
 def gru_backward_small(k, gates, ghn, hs, h0, h0_stride, w_hh, w_lin, dpred, dh_last, dhs, dw_hh, db_hh, db_ih, dw_lin, db_lin,
-                       dh0, P, T, B, ws, ws_dwhh):
-    """BPTT of a small head set: low-latency kernel + tcgen05 dW_hh GEMM when the batch allows, else the exact kernel."""
+                       dh0, P, T, B, ws, ws_dwhh, split_dwhh=False):
+    """BPTT of a small head set: MMA / low-latency kernel + tcgen05 dW_hh GEMM when the batch allows, else the exact kernel.
+    split_dwhh=True: when dW_hh is a separate GEMM it is NOT launched; a callable that launches it is returned instead, so the
+    caller can put it on another stream next to the projection weight gradient (both only read the BPTT's outputs)."""
     if (has_ll(k) or has_mma(k)) and hasattr(k, "gru_dwhh_tc") and B % 32 == 0 and ws_dwhh is not None:
-        bwd = k.gru_bwd_mma if has_mma(k) else k.gru_bwd_ll
+        bwd = k.gru_bwd_mma if mma_bwd_preferred(k, P, B) else k.gru_bwd_ll
         bwd(gates, ghn, hs, h0, h0_stride, w_hh, w_lin, dpred, dh_last, dhs, db_hh, db_ih, dw_lin, db_lin, dh0, P, T, B, ws)
-        k.gru_dwhh_tc(gates, ghn, hs, h0, h0_stride, dw_hh, P, T, B, ws_dwhh)
+        dwhh = lambda: k.gru_dwhh_tc(gates, ghn, hs, h0, h0_stride, dw_hh, P, T, B, ws_dwhh)
+        if split_dwhh:
+            return dwhh
+        dwhh()
     else:
         k.gru_bwd(gates, ghn, hs, h0, h0_stride, w_hh, w_lin, dpred, dh_last, dhs, dw_hh, db_hh, db_ih, dw_lin, db_lin, dh0, P, T, B, ws)
+    return None
