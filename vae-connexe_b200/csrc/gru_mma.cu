@@ -895,37 +895,43 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Warp-specialised BPTT (dW_hh deferred): the mirror image of gru_fwd_mma_ws_kernel.
-//   * warps 0-7, "M": hold W_hh [192 x 64] as B fragments (n-tile = the warp's 8 hidden units, 24 k-steps), wait for a
-//     tile's gate-gradient operand dgh = [da_r | da_z | da_n*r] (16 x 192, fragment order), issue its 72 MMAs
-//     (3xTF32, one accumulator per term) and hand dgh . W_hh to their partner warp through shared memory;
-//   * warps 8-15, "P": cell backward at 4 elements per thread (dh_t = dh_{t+1}*z + dgh.W_hh arrives from M), staging of
-//     dgi (in place over r|z|n), dgh_n (in place over gh_n) and of the next operand, the column sums
-//     (db_ih, db_hh, dw_lin, db_lin: 11 register accumulators per tile, reduced in fixed order), TMA plumbing.
-// Per step a stream's inputs -- r|z|n (12 KB), gh_n, h_{t-1} (and dhs) tiles -- arrive by TMA into a 3-deep ring on one
-// mbarrier; dgi / dgh_n leave by TMA.  Two tiles of one head per CTA (streams a, b) once there are more tiles than SMs.
+// Warp-specialised BPTT (dW_hh deferred): the mirror image of gru_fwd_mma_ws_kernel, with the product split over K.
+//   dh_{t-1} = dh_t * z + dgh . W_hh,   dgh = [da_r | da_z | da_n*r]  (16 x 192),  W_hh [192 x 64]
+//   * warps 0-7, "M": warp w owns the K-SLICE of its 8 hidden units (3 gates x 8 = 24 of the 192 reduction indices) for ALL 64
+//     outputs: W_hh rows of the slice as B fragments (3 k-steps x 8 n-tiles, 96 registers); its A operand is exactly what
+//     the partner thread (same lane) of P warp w computes -- handed over pre-split into tf32 hi | lo as six 128-bit words,
+//     so an M op is 6 LDS + 72 HMMA (8 independent accumulator chains) + 8 STS; the 16 x 64 partial product goes to shared
+//     memory;
+//   * warps 8-15, "P": cell backward at 4 elements per thread; dh_{t-1} = dh_t*z + the 8 partials summed in fixed order
+//     (deterministic); staging of dgi (in place over r|z|n), dgh_n (in place over gh_n) and of the next operand; the
+//     column sums (db_ih, db_hh, dw_lin, db_lin: 11 register accumulators per tile, reduced in fixed order); TMA plumbing.
+//   (A first version split N instead -- every M warp reading the whole 12 KB operand and splitting it itself: 24 LDS + 288
+//   ALU + 72 HMMA per op, M-bound at 3.8 us per step.)
+// Per step a stream's inputs -- r|z|n (12 KB), gh_n, h_{t-1} (and dhs) tiles -- arrive by TMA into a ring on one mbarrier; dgi /
+// dgh_n leave by TMA.  Two tiles of one head per CTA (streams a, b; 2-deep rings) once there are more tiles than SMs, else
+// one stream with 3-deep rings.
 // ------------------------------------------------------------------------------------------------------------
+template <int NS>
 struct __align__(1024) BwdStreamSmem {
-    float slab[PF_NS][M_ROWS * MG];        // r|z|n -> dgi                      [row][6 x 128 B] swizzled
-    float gn[PF_NS][M_ROWS * MH];          // gh_n -> dgh_n                     [row][2 x 128 B] swizzled
-    float hp[PF_NS][M_ROWS * MH];          // h_{t-1}
-    float de[PF_NS][M_ROWS * MH];          // dhs (per-step gradient into h_t), when present
-    float dgh[2][M_ROWS * MG];             // the A operand of the step, fragment order (frag_idx), by step parity
-    float accb[8][32 * 4];                 // dgh . W_hh of the warp's units, [M warp][lane] x float4 (C-fragment order)
-    uint64_t in_full[PF_NS];
+    float slab[NS][M_ROWS * MG];           // r|z|n -> dgi                      [row][6 x 128 B] swizzled
+    float gn[NS][M_ROWS * MH];             // gh_n -> dgh_n                     [row][2 x 128 B] swizzled
+    float hp[NS][M_ROWS * MH];             // h_{t-1}
+    float de[NS][M_ROWS * MH];             // dhs (per-step gradient into h_t), when present
+    float dghb[8][3][2][32 * 4];           // A operand: [warp][gate][hi | lo][lane] x 4 words (the lane's MMA fragment)
+    float accb[8][8][32 * 4];              // partial products: [M warp][n-tile][lane] x float4 (C-fragment order)
+    uint64_t in_full[NS];
     uint64_t dgh_ready;
-    uint64_t acc_ready[8];
+    uint64_t acc_ready;
 };
-struct __align__(1024) BwdPipeSmem { BwdStreamSmem st[2]; };
 
 struct BwdTmaps { CUtensorMap g, n, h, z, d; };
 
-template <bool HAS_DHS>
+template <bool HAS_DHS, int NS>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int pf, int npph, int h0_per_head) {
     using namespace umma;
     extern __shared__ __align__(1024) uint8_t mma_smem_raw[];
-    BwdPipeSmem& sm = *reinterpret_cast<BwdPipeSmem*>(mma_smem_raw);
+    BwdStreamSmem<NS>* sms = reinterpret_cast<BwdStreamSmem<NS>*>(mma_smem_raw);      // pf streams
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int w = warp & 7;
@@ -956,13 +962,11 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
     };
 
     if (tid == 0) {
+        for (int s = 0; s < pf; ++s) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-#pragma unroll
-            for (int i = 0; i < PF_NS; ++i) mbar_init(&sm.st[s].in_full[i], 1);
-            mbar_init(&sm.st[s].dgh_ready, 1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) mbar_init(&sm.st[s].acc_ready[i], 1);
+            for (int i = 0; i < NS; ++i) mbar_init(&sms[s].in_full[i], 1);
+            mbar_init(&sms[s].dgh_ready, 1);
+            mbar_init(&sms[s].acc_ready, 8);
         }
         fence_barrier_init();
     }
@@ -970,18 +974,19 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
 
     if (is_m) {
         // =============================================================== M warps ===============================================================
-        uint32_t bhi[24][2], blo[24][2];
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(160));       // W_hh 96 + accumulators 32 + operand 24 (the P warps give up 32 each)
+        uint32_t bhi[3][8][2], blo[3][8][2];
         int cur_head = -1;
-        auto load_head = [&](int head) {          // B[k][n] = W_hh[k][8w + n]; k-step ks, k-slots q / q+4 <-> k = 2p, 2p+1, p = 8*(ks/2) + 2q + ks%2
-            const float* __restrict__ W = a.w_hh + (long long)head * MG * MH + 8 * w + g;
+        auto load_head = [&](int head) {          // k-step `gate`: k-slots q / q+4 <-> W_hh rows gate*64 + 8w + 2q (+1); n-tile j column g <-> output unit 8j + g
+            const float* __restrict__ W = a.w_hh + (long long)head * MG * MH;
 #pragma unroll
-            for (int c = 0; c < 12; ++c) {
-                const float* p = W + (long long)(16 * c + 4 * q) * MH;
-                const float v0 = __ldg(p), v1 = __ldg(p + MH), v2 = __ldg(p + 2 * MH), v3 = __ldg(p + 3 * MH);
-                split_tf32_fast(v0, bhi[2 * c][0], blo[2 * c][0]);
-                split_tf32_fast(v1, bhi[2 * c][1], blo[2 * c][1]);
-                split_tf32_fast(v2, bhi[2 * c + 1][0], blo[2 * c + 1][0]);
-                split_tf32_fast(v3, bhi[2 * c + 1][1], blo[2 * c + 1][1]);
+            for (int gate = 0; gate < 3; ++gate) {
+                const float* r0 = W + (long long)(gate * MH + 8 * w + 2 * q) * MH + g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    split_tf32_fast(__ldg(r0 + 8 * j), bhi[gate][j][0], blo[gate][j][0]);
+                    split_tf32_fast(__ldg(r0 + MH + 8 * j), bhi[gate][j][1], blo[gate][j][1]);
+                }
             }
             cur_head = head;
         };
@@ -990,41 +995,38 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
         for (int n = 0; n < nsteps; ++n) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
+                if (s == 1 && pf == 1) break;
                 if (pos[s].vrows > 0) {
                     if (pos[s].head != cur_head) load_head(pos[s].head);
-                    BwdStreamSmem& st = sm.st[s];
+                    BwdStreamSmem<NS>& st = sms[s];
                     mbar_wait(&st.dgh_ready, cnt[s] & 1u);
-                    const float* db = st.dgh[cnt[s] & 1];
-                    float acc[3][4];
+                    uint4 ah[3], al[3];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[k][e] = 0.f;
-#pragma unroll
-                    for (int grp = 0; grp < 6; ++grp) {
-                        float4 av[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int ks = 4 * grp + k;
-                            av[k] = *reinterpret_cast<const float4*>(&db[frag_idx(8 * (ks >> 1) + 2 * q + (ks & 1), g)]);
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int ks = 4 * grp + k;
-                            uint32_t ahi[4], alo[4];
-                            split_tf32_fast(av[k].x, ahi[0], alo[0]); split_tf32_fast(av[k].y, ahi[1], alo[1]);
-                            split_tf32_fast(av[k].z, ahi[2], alo[2]); split_tf32_fast(av[k].w, ahi[3], alo[3]);
-                            mma_tf32(acc[0], alo, bhi[ks]);
-                            mma_tf32(acc[1], ahi, blo[ks]);
-                            mma_tf32(acc[2], ahi, bhi[ks]);
-                        }
+                    for (int gate = 0; gate < 3; ++gate) {
+                        ah[gate] = *reinterpret_cast<const uint4*>(&st.dghb[w][gate][0][lane * 4]);
+                        al[gate] = *reinterpret_cast<const uint4*>(&st.dghb[w][gate][1][lane * 4]);
                     }
-                    float4 o;
-                    o.x = __fadd_rn(__fadd_rn(acc[0][0], acc[1][0]), acc[2][0]); o.y = __fadd_rn(__fadd_rn(acc[0][1], acc[1][1]), acc[2][1]);
-                    o.z = __fadd_rn(__fadd_rn(acc[0][2], acc[1][2]), acc[2][2]); o.w = __fadd_rn(__fadd_rn(acc[0][3], acc[1][3]), acc[2][3]);
-                    *reinterpret_cast<float4*>(&st.accb[w][lane * 4]) = o;
+                    float acc[8][4];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+                    for (int gate = 0; gate < 3; ++gate) {
+                        const uint32_t ahi[4] = {ah[gate].x, ah[gate].y, ah[gate].z, ah[gate].w};
+                        const uint32_t alo[4] = {al[gate].x, al[gate].y, al[gate].z, al[gate].w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) mma_tf32(acc[j], alo, bhi[gate][j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) mma_tf32(acc[j], ahi, blo[gate][j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) mma_tf32(acc[j], ahi, bhi[gate][j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(&st.accb[w][j][lane * 4]) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&st.acc_ready[w]);
+                    if (lane == 0) mbar_arrive(&st.acc_ready);
                     ++cnt[s];
                 }
                 advance(pos[s], s);
@@ -1032,6 +1034,7 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
         }
     } else {
         // =============================================================== P warps ===============================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(96));
         const int ptid = tid - 256;
         float wl[2] = {0.f, 0.f};
         int cur_head = -1;
@@ -1047,8 +1050,8 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
             const int j = n / T;
             FwdPos p = pos_of_pair(j, s);
             p.t = T - 1 - (n - j * T);
-            const int slot = n % PF_NS;
-            BwdStreamSmem& st = sm.st[s];
+            const int slot = n % NS;
+            BwdStreamSmem<NS>& st = sms[s];
             mbar_arrive_expect_tx(&st.in_full[slot], p.vrows > 0 ? IN_BYTES : 0u);
             if (p.vrows > 0) {
                 const int c2 = p.tile * M_ROWS, c3 = p.head * T + p.t;
@@ -1064,11 +1067,11 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
             else         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (p.vrows > 0) {
                 const int c2 = p.tile * M_ROWS, c3 = p.head * T + p.t;
-                tma_store_4d(&tm.g, sm.st[s].slab[n % PF_NS], 0, 0, c2, c3);
-                tma_store_4d(&tm.n, sm.st[s].gn[n % PF_NS], 0, 0, c2, c3);
+                tma_store_4d(&tm.g, sms[s].slab[n % NS], 0, 0, c2, c3);
+                tma_store_4d(&tm.n, sms[s].gn[n % NS], 0, 0, c2, c3);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (n >= 1 && n - 1 + PF_NS < nsteps) issue_load(s, n - 1 + PF_NS);
+            if (n >= 1 && n - 1 + NS < nsteps) issue_load(s, n - 1 + NS);
         };
         auto load_dp = [&](float (&dp)[2], const FwdPos& p) {
 #pragma unroll
@@ -1095,21 +1098,18 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
             o_r[i] = sw_idx(6, g + 8 * i, ucol); o_z[i] = sw_idx(6, g + 8 * i, MH + ucol); o_n[i] = sw_idx(6, g + 8 * i, 2 * MH + ucol);
             o_h[i] = sw_idx(2, g + 8 * i, ucol);
         }
-        const int o_frag = frag_idx(4 * w + q, g);
         FwdPos pos[2] = {pos_of_pair(0, 0), pos_of_pair(0, 1)};
         // per-stream state
         float dh[2][2][2], dhz[2][2][2];          // [stream][row][unit]
         float2 hcur[2][2];                        // h_t of the step being processed (dw_lin += dpred[t] * h_t)
         float dpn[2][2];                          // dpred of the stream's next step (prefetched)
-        float2 dhl[2][2], hl[2][2];               // next tile's dh_last / h_{T-1} (prefetched during the last step of a tile)
         float sums[2][11];                        // db_ih r,z,n (x2 units) | db_hh n (x2) | dw_lin (x2) | db_lin
         bool pending[2] = {false, false};         // an MMA result of this stream is outstanding
         FwdPos ppos[2] = {pos[0], pos[1]};        // position of the outstanding step
-        uint32_t cnt[2] = {0, 0}, dcnt[2] = {0, 0};
+        uint32_t cnt[2] = {0, 0};
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             load_dp(dpn[s], pos[s]);
-            load_tile_start(dhl[s], hl[s], pos[s]);
 #pragma unroll
             for (int k = 0; k < 11; ++k) sums[s][k] = 0.f;
 #pragma unroll
@@ -1117,16 +1117,21 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
         }
         load_head(pos[0].head);
         if (ptid == 0) {
-            for (int n = 0; n < PF_NS && n < nsteps; ++n) { issue_load(0, n); if (pf == 2) issue_load(1, n); }
+            for (int n = 0; n < NS && n < nsteps; ++n) { issue_load(0, n); if (pf == 2) issue_load(1, n); }
         }
         // finish the outstanding step of stream s: dh_{t-1} = dh_t * z + dgh . W_hh; at a tile end write dh0 and the tile's column sums
         auto finish = [&](int s) {
-            BwdStreamSmem& st = sm.st[s];
-            mbar_wait(&st.acc_ready[w], cnt[s] & 1u);
+            BwdStreamSmem<NS>& st = sms[s];
+            mbar_wait(&st.acc_ready, cnt[s] & 1u);
             ++cnt[s];
-            const float4 v = *reinterpret_cast<const float4*>(&st.accb[w][lane * 4]);
-            dh[s][0][0] = __fadd_rn(dhz[s][0][0], v.x); dh[s][0][1] = __fadd_rn(dhz[s][0][1], v.y);
-            dh[s][1][0] = __fadd_rn(dhz[s][1][0], v.z); dh[s][1][1] = __fadd_rn(dhz[s][1][1], v.w);
+            float4 sum = *reinterpret_cast<const float4*>(&st.accb[0][w][lane * 4]);
+#pragma unroll
+            for (int v = 1; v < 8; ++v) {         // the 8 K-slices, fixed order
+                const float4 x = *reinterpret_cast<const float4*>(&st.accb[v][w][lane * 4]);
+                sum.x = __fadd_rn(sum.x, x.x); sum.y = __fadd_rn(sum.y, x.y); sum.z = __fadd_rn(sum.z, x.z); sum.w = __fadd_rn(sum.w, x.w);
+            }
+            dh[s][0][0] = __fadd_rn(dhz[s][0][0], sum.x); dh[s][0][1] = __fadd_rn(dhz[s][0][1], sum.y);
+            dh[s][1][0] = __fadd_rn(dhz[s][1][0], sum.z); dh[s][1][1] = __fadd_rn(dhz[s][1][1], sum.w);
             pending[s] = false;
             const FwdPos& p = ppos[s];
             if (p.t == 0) {                       // tile end
@@ -1164,25 +1169,24 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (s == 1 && pf == 1) break;
-                BwdStreamSmem& st = sm.st[s];
+                BwdStreamSmem<NS>& st = sms[s];
                 const FwdPos pp = pos[s];
                 FwdPos nx = pp;
                 advance(nx, s);
                 if (pending[s]) finish(s);
                 if (pp.vrows > 0) {
                     if (pp.head != cur_head) load_head(pp.head);
-                    if (pp.t == T - 1) {          // tile start
+                    if (pp.t == T - 1) {          // tile start: dh_last, h_{T-1}
+                        float2 dhl[2], hl[2];
+                        load_tile_start(dhl, hl, pp);
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) { dh[s][i][0] = dhl[s][i].x; dh[s][i][1] = dhl[s][i].y; hcur[s][i] = hl[s][i]; }
+                        for (int i = 0; i < 2; ++i) { dh[s][i][0] = dhl[i].x; dh[s][i][1] = dhl[i].y; hcur[s][i] = hl[i]; }
                     }
                     const float dp[2] = {dpn[s][0], dpn[s][1]};
                     // prefetch for the stream's next step
-                    if (nx.vrows > 0) {
-                        load_dp(dpn[s], nx);
-                        if (nx.t == T - 1) load_tile_start(dhl[s], hl[s], nx);
-                    }
-                    const int slot = n % PF_NS;
-                    mbar_wait(&st.in_full[slot], (uint32_t)(n / PF_NS) & 1u);
+                    if (nx.vrows > 0) load_dp(dpn[s], nx);
+                    const int slot = n % NS;
+                    mbar_wait(&st.in_full[slot], (uint32_t)(n / NS) & 1u);
                     float* slab = st.slab[slot];
                     float* gns = st.gn[slot];
                     const float* hps = st.hp[slot];
@@ -1223,16 +1227,27 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
                         fz[i] = daz[0]; fz[2 + i] = daz[1];
                         fn_[i] = dgn[0]; fn_[2 + i] = dgn[1];
                     }
-                    float* db = st.dgh[dcnt[s] & 1];
-                    ++dcnt[s];
-                    *reinterpret_cast<float4*>(db + o_frag) = make_float4(fr[0], fr[1], fr[2], fr[3]);
-                    *reinterpret_cast<float4*>(db + o_frag + 32 * 32) = make_float4(fz[0], fz[1], fz[2], fz[3]);            // frag_idx(32 + p, g) = frag_idx(p, g) + 32*8*4
-                    *reinterpret_cast<float4*>(db + o_frag + 64 * 32) = make_float4(fn_[0], fn_[1], fn_[2], fn_[3]);
+                    // the partner lane's A fragments {x[g][u], x[g+8][u], x[g][u+1], x[g+8][u+1]} of the three gate blocks, split hi | lo
+                    {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split_tf32_fast(fr[e], hi[e], lo[e]);
+                        *reinterpret_cast<uint4*>(&st.dghb[w][0][0][lane * 4]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(&st.dghb[w][0][1][lane * 4]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split_tf32_fast(fz[e], hi[e], lo[e]);
+                        *reinterpret_cast<uint4*>(&st.dghb[w][1][0][lane * 4]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(&st.dghb[w][1][1][lane * 4]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split_tf32_fast(fn_[e], hi[e], lo[e]);
+                        *reinterpret_cast<uint4*>(&st.dghb[w][2][0][lane * 4]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(&st.dghb[w][2][1][lane * 4]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
                     fence_proxy_async_smem();
                     pending[s] = true;
                     ppos[s] = pp;
                 }
-                p_warps_sync();
+                p_warps_sync();                   // every P warp has read the previous partials and staged its operand: M may overwrite accb
                 if (ptid == 0) {
                     if (pp.vrows > 0) mbar_arrive(&st.dgh_ready);
                     plumb(s, n, pp);
@@ -1364,16 +1379,25 @@ extern "C" int crvae_gru_bwd_mma(float* gates, float* ghn, const float* hs, cons
         const uint64_t dz[4] = {32, 2, (uint64_t)B, (uint64_t)(per_head ? P : 1)};
         const uint64_t sz[3] = {128, (uint64_t)MH * 4, (uint64_t)(per_head ? h0_head_stride : (int64_t)B * MH) * 4};
         if ((rc = make_tmap_generic(&tm.z, h0, 4, dz, sz, bh, false))) return rc;
-        const int smem = (int)sizeof(BwdPipeSmem);
+        // one stream: 3-deep rings; two streams: 2-deep rings (shared memory)
+        const int smem = pf == 1 ? (int)sizeof(BwdStreamSmem<3>) : 2 * (int)sizeof(BwdStreamSmem<2>);
         static bool attr_done = false;
         if (!attr_done) {
-            cudaError_t e1 = cudaFuncSetAttribute(gru_bwd_mma_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            cudaError_t e2 = cudaFuncSetAttribute(gru_bwd_mma_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("gru_bwd_mma_ws smem attr (%d B): %s", smem, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return (int)(e1 != cudaSuccess ? e1 : e2); }
+            const int s3 = (int)sizeof(BwdStreamSmem<3>), s2 = 2 * (int)sizeof(BwdStreamSmem<2>);
+            cudaError_t e = cudaFuncSetAttribute(gru_bwd_mma_ws_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, s3);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gru_bwd_mma_ws_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, s3);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gru_bwd_mma_ws_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gru_bwd_mma_ws_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+            if (e != cudaSuccess) { set_error("gru_bwd_mma_ws smem attr (%d / %d B): %s", s3, s2, cudaGetErrorString(e)); return (int)e; }
             attr_done = true;
         }
-        if (dhs) gru_bwd_mma_ws_kernel<true><<<wgrid, WS_THREADS, smem, st>>>(tm, a, pf, npph, per_head);
-        else     gru_bwd_mma_ws_kernel<false><<<wgrid, WS_THREADS, smem, st>>>(tm, a, pf, npph, per_head);
+        if (pf == 1) {
+            if (dhs) gru_bwd_mma_ws_kernel<true, 3><<<wgrid, WS_THREADS, smem, st>>>(tm, a, pf, npph, per_head);
+            else     gru_bwd_mma_ws_kernel<false, 3><<<wgrid, WS_THREADS, smem, st>>>(tm, a, pf, npph, per_head);
+        } else {
+            if (dhs) gru_bwd_mma_ws_kernel<true, 2><<<wgrid, WS_THREADS, smem, st>>>(tm, a, pf, npph, per_head);
+            else     gru_bwd_mma_ws_kernel<false, 2><<<wgrid, WS_THREADS, smem, st>>>(tm, a, pf, npph, per_head);
+        }
         rc = check_launch("gru_bwd_mma_ws_kernel");
     }
     if (rc) return rc;

@@ -355,8 +355,8 @@ class CRVAEEngine:
         # (crvae_gru_dwhh_tc, issued below next to the projection weight gradient); the BPTT itself runs on tcgen05
         # (crvae_gru_bwd_tc) when the rank holds >= 8 heads, else on the exact FFMA2 kernels.
         defer = (P >= 8 or self.rec_mode in ("ll", "mma")) and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
-        if P > 0 and defer and self.rec_mode in ("ll", "mma"):
-            bwd = k.gru_bwd_mma if (self.rec_mode == "mma" and R.mma_bwd_preferred(k, P, B)) else k.gru_bwd_ll
+        if P > 0 and defer and (self.rec_mode in ("ll", "mma") or (self.rec_mode == "tc3" and R.mma_bwd_preferred(k, P, B))):
+            bwd = k.gru_bwd_mma if R.mma_bwd_preferred(k, P, B) else k.gru_bwd_ll
             bwd(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
                 g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
         elif P > 0 and defer and self.rec_mode == "tc3" and hasattr(k, "gru_bwd_tc"):
@@ -498,12 +498,12 @@ class CRVAEEngine:
     def _flow_bwd_group(self, lo, hi, ws):
         k, th, g, B = self.k, self.theta, self.grad, self.B
         n, sl = hi - lo, slice(lo, hi)
-        fn = k.gru_bwd_tc if self.rec_mode == "tc3" else None
+        fn = k.gru_bwd_tc if (self.rec_mode == "tc3" and not R.mma_bwd_preferred(k, n, B)) else None
         if fn is not None:
             fn(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None,
                g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
         else:
-            bwd = k.gru_bwd_mma if (self.rec_mode == "mma" and R.mma_bwd_preferred(k, n, B)) else k.gru_bwd_ll
+            bwd = k.gru_bwd_mma if R.mma_bwd_preferred(k, n, B) else k.gru_bwd_ll
             bwd(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None, None,
                 g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
 

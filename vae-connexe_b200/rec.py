@@ -35,14 +35,14 @@ def mma_preferred(P: int) -> bool:
     return MMA_MODE == "1" or (MMA_MODE == "small" and P <= MMA_MAX_HEADS)
 
 
-# BPTT: the warp-specialised MMA kernel wins up to ~320 16-row tiles (B = 256, T = 10, us: P = 1: ll 42.1, mma 37.9; P = 13: ll 66.4,
-# mma 56.1; P = 25: ll 91.1, mma 99.3; P = 50: ll 163, mma 142, tcgen05 110), the exact low-latency kernel between that and the
-# tcgen05 range
-MMA_BWD_MAX_TILES = int(os.environ.get("CRVAE_MMA_BWD_MAX_TILES", "320"))
+# BPTT: the warp-specialised K-split MMA kernel is the fastest BPTT from one head up to ~100 heads (B = 256, T = 10, us:
+# P = 1: ll 42.0, mma 29.5; P = 13: ll 66.4, mma 41.8, tcgen05 64; P = 50: mma 105.5, tcgen05 110; P = 100: mma 193.5, tcgen05 201.7);
+# beyond that the tcgen05 kernel's many full waves win (p = 1000: 149 us per 100 heads).
+MMA_BWD_MAX_TILES = int(os.environ.get("CRVAE_MMA_BWD_MAX_TILES", "1700"))
 
 
 def mma_bwd_preferred(k, P: int, B: int) -> bool:
-    return has_mma(k) and (MMA_MODE == "1" or not has_ll(k) or P * ((B + 15) // 16) <= MMA_BWD_MAX_TILES)
+    return has_mma(k) and (MMA_MODE == "1" or P * ((B + 15) // 16) <= MMA_BWD_MAX_TILES)
 
 
 def has_ll(k) -> bool:
