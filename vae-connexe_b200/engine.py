@@ -498,7 +498,10 @@ class CRVAEEngine:
     def _flow_bwd_group(self, lo, hi, ws):
         k, th, g, B = self.k, self.theta, self.grad, self.B
         n, sl = hi - lo, slice(lo, hi)
-        fn = k.gru_bwd_tc if (self.rec_mode == "tc3" and not R.mma_bwd_preferred(k, n, B)) else None
+        # (several head groups run side by side on their own streams; the persistent MMA grid would take every SM and serialise
+        # them -- measured at p = 100, two groups of 50: 0.537 ms per iteration against 0.516 with the tcgen05 BPTT)
+        grouped = len(self._flow["groups"]) > 1
+        fn = k.gru_bwd_tc if (self.rec_mode == "tc3" and (grouped or not R.mma_bwd_preferred(k, n, B))) else None
         if fn is not None:
             fn(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None,
                g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
