@@ -1,0 +1,10 @@
+cd $GRAFT_REPO_ROOT
+CMD="python bench.py --steps 3 --warmup 3 --lean --no-cpu-baseline"
+$CMD > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02c_launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+tail -2 gpurun_out/ncu_launch.log
+export P=13 T=10 B=256
+python tools/prof_mma.py > gpurun_out/prof_mma_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"gru_fwd_mma|gru_bwd_mma" -s 2 -c 2 -o gpurun_out/r02c_prof_mma_p13 python tools/prof_mma.py > gpurun_out/prof_mma_ncu.log 2>&1
+tail -2 gpurun_out/prof_mma_ncu.log
+export P=100
+python tools/prof_mma.py > gpurun_out/prof_mma_plain.log 2>&1 && ncu --set full --clock-control none -k regex:"gru_fwd_mma|gru_bwd_mma" -s 2 -c 2 -o gpurun_out/r02c_prof_mma_p100 python tools/prof_mma.py > gpurun_out/prof_mma_ncu.log 2>&1
+tail -2 gpurun_out/prof_mma_ncu.log

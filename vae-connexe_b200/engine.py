@@ -355,8 +355,8 @@ class CRVAEEngine:
         # (crvae_gru_dwhh_tc, issued below next to the projection weight gradient); the BPTT itself runs on tcgen05
         # (crvae_gru_bwd_tc) when the rank holds >= 8 heads, else on the exact FFMA2 kernels.
         defer = (P >= 8 or self.rec_mode in ("ll", "mma")) and B % 32 == 0 and hasattr(k, "gru_dwhh_tc") and self.bwd_mode == "defer"
-        if P > 0 and defer and (self.rec_mode in ("ll", "mma") or (self.rec_mode == "tc3" and R.mma_bwd_preferred(k, P, B))):
-            bwd = k.gru_bwd_mma if R.mma_bwd_preferred(k, P, B) else k.gru_bwd_ll
+        if P > 0 and defer and (self.rec_mode in ("ll", "mma") or (self.rec_mode == "tc3" and self._bwd_mma(P))):
+            bwd = k.gru_bwd_mma if self._bwd_mma(P) else k.gru_bwd_ll
             bwd(self.gates, self.ghn, self.hs, self.zlat, 0, th["w_hh"], th["w_lin"], self.dpred, None, None,
                 g["b_hh"], g["b_ih"], g["w_lin"], g["b_lin"], self.dh0, P, DEC_STEPS, B, self.ws_gru)
         elif P > 0 and defer and self.rec_mode == "tc3" and hasattr(k, "gru_bwd_tc"):
@@ -456,6 +456,20 @@ class CRVAEEngine:
                 and self.proj_mode == "tc3" and self.rec_mode in ("tc3", "ll", "mma") and self.bwd_mode == "defer"
                 and hasattr(k, "gru_dwhh_tc") and self.ws_lat is not None and self.use_side_stream)
 
+    def _auto_grouped(self) -> bool:
+        """Two equal head groups whenever the 128-row recurrent grid is more than one wave but not many: measured at p = 100
+        (200 tiles, ms per iteration): one group 0.612, 74+26 0.549, 50+50 0.523, 34+33+33 0.543, 4x25 0.551, 5x20 0.557."""
+        tiles = ((self.B or 0) + 127) // 128
+        return self.rec_mode == "tc3" and self.P >= 16 and 148 < self.P * tiles <= 4 * 148
+
+    def _bwd_mma(self, n_heads: int) -> bool:
+        """The K-split MMA BPTT for a launch over n_heads heads?  Not where the flow runs head groups side by side: its
+        persistent grid would take every SM and serialise them (p = 100, two groups of 50: 0.537 ms per iteration against
+        0.516 with the tcgen05 BPTT).  One decision for the eager and the captured iteration."""
+        import os as _os
+        grouped = self._auto_grouped() if _os.environ.get("CRVAE_GROUPS", "auto") == "auto" else True
+        return R.mma_bwd_preferred(self.k, n_heads, self.B) and not (self.rec_mode == "tc3" and grouped)
+
     def _flow_setup(self):
         if getattr(self, "_flow", None) is not None and self._flow["B"] == self.B:
             return self._flow
@@ -463,10 +477,7 @@ class CRVAEEngine:
         P, B, k, dev = self.P, self.B, self.k, self.device
         spec = _os.environ.get("CRVAE_GROUPS", "auto")
         if spec == "auto":
-            tiles = (B + 127) // 128
-            # two equal groups whenever the 128-row recurrent grid is more than one wave but not many: measured at p = 100
-            # (200 tiles, ms per iteration): one group 0.612, 74+26 0.549, 50+50 0.523, 34+33+33 0.543, 4x25 0.551, 5x20 0.557
-            sizes = [P // 2, P - P // 2] if (self.rec_mode == "tc3" and P >= 16 and 148 < P * tiles <= 4 * 148) else [P]
+            sizes = [P // 2, P - P // 2] if self._auto_grouped() else [P]
         else:
             sizes = [int(x) for x in spec.split(",") if x]
             if sum(sizes) != P or min(sizes) <= 0:
@@ -498,15 +509,12 @@ class CRVAEEngine:
     def _flow_bwd_group(self, lo, hi, ws):
         k, th, g, B = self.k, self.theta, self.grad, self.B
         n, sl = hi - lo, slice(lo, hi)
-        # (several head groups run side by side on their own streams; the persistent MMA grid would take every SM and serialise
-        # them -- measured at p = 100, two groups of 50: 0.537 ms per iteration against 0.516 with the tcgen05 BPTT)
-        grouped = len(self._flow["groups"]) > 1
-        fn = k.gru_bwd_tc if (self.rec_mode == "tc3" and (grouped or not R.mma_bwd_preferred(k, n, B))) else None
+        fn = k.gru_bwd_tc if (self.rec_mode == "tc3" and not self._bwd_mma(n)) else None
         if fn is not None:
             fn(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None,
                g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
         else:
-            bwd = k.gru_bwd_mma if R.mma_bwd_preferred(k, n, B) else k.gru_bwd_ll
+            bwd = k.gru_bwd_mma if self._bwd_mma(n) else k.gru_bwd_ll
             bwd(self.gates[sl], self.ghn[sl], self.hs[sl], self.zlat, 0, th["w_hh"][sl], th["w_lin"][sl], self.dpred[sl], None, None,
                 g["b_hh"][sl], g["b_ih"][sl], g["w_lin"][sl], g["b_lin"][sl], self.dh0[sl], n, DEC_STEPS, B, ws["gru"])
 
