@@ -198,6 +198,8 @@ def test_gru_forward_tensor_core(P, T, B, lin, t_skip, shared_h0):
     (30, 3, 144, True, 1, True, False, False),       # 270 tiles > 148 SMs: persistent CTAs cross tile and head boundaries
     (12, 4, 200, True, 0, False, False, False),      # 156 tiles: tile pairs, odd tile count per head (idle second stream), ragged last tile
     (22, 10, 256, True, 1, True, False, False),      # 176 tile pairs on 148 CTAs: head boundaries inside a CTA's range at a zero-input step
+    (20, 4, 256, True, 0, False, True, True),        # tile pairs with per-head h0, dh_last and per-step dhs (2-deep rings of the MMA BPTT)
+    (40, 1, 80, True, 0, True, True, False),         # 200 tiles of a single step: every step is a tile start and a tile end
 ])
 @pytest.mark.parametrize("family", ["ll", "mma"])
 def test_gru_low_latency_forward_backward(P, T, B, lin, t_skip, shared_h0, last, with_dhs, family):
