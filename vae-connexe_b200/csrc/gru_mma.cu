@@ -27,6 +27,7 @@
 // crvae_gru_dwhh_tc).
 #include "common.cuh"
 #include "umma.cuh"
+#include <cuda_fp16.h>
 #include <type_traits>
 #include <cstdlib>
 
@@ -70,6 +71,20 @@ __device__ __forceinline__ void split_tf32_fast(float v, uint32_t& hi, uint32_t&
 // thread (g, q) of warp w produces for its unit pair.  The row-group index is XORed with the consumer's quad lane so that the
 // 8 lanes of a quarter warp (2 row groups x 4 quad lanes) hit 8 different 16-byte bank groups.
 __device__ __forceinline__ int frag_idx(int p, int g) { return (p * 8 + (g ^ (((p >> 1) & 3) << 1))) * 4; }
+// fp16 hi | lo split of a finite value of moderate magnitude (hidden states, recurrent weights): hi = fp16(v), lo = fp16((v - hi) * 2^11).
+// fp16 x fp16 products are exact in the fp32 accumulator; the cross terms are accumulated apart and scaled back by 2^-11, so the
+// result carries 22 significant bits like 3xTF32 -- at half the MMA count (m16n8k16 covers 16 reduction indices per issue slot).
+__device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const __half2 l = __floats2half2_rn((x - __low2float(h)) * 2048.f, (y - __high2float(h)) * 2048.f);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 __device__ __forceinline__ float2 ldg2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void stg2(float* p, float x, float y) { *reinterpret_cast<float2*>(p) = make_float2(x, y); }
 
@@ -558,6 +573,7 @@ __device__ long long g_mma_dbg[16 * 8];            // per-warp cycle counters of
 #endif
 struct FwdPos { int j, head, tile, t, vrows; };   // (uniform) a stream's step: pair index in the CTA's range, head, tile, step; vrows == 0: idle
 
+template <bool F16>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmN,
                       GruMmaFwdArgs a, int pf, int npph) {
@@ -608,20 +624,31 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         // =============================================================== M warps ===============================================================
         // B fragments of W_hh^T: n-tile `gate` column g <-> gate row gate*64 + 8w + g; k-step s, k-slots q / q+4 <-> units 2p, 2p+1 with
         // p = 8*(s/2) + 2q + (s%2)  (the pair whose A fragment frag_idx(p, g) holds)
-        uint32_t bhi[3][8][2], blo[3][8][2];
+        uint32_t bhi[3][8][2], blo[3][8][2];      // (fp16 form: k-steps 0..3 only)
         int cur_head = -1;
         auto load_head = [&](int head) {
             const float* __restrict__ W = a.w_hh + (long long)head * MG * MH;
 #pragma unroll
             for (int gate = 0; gate < 3; ++gate) {
-                const float* row = W + (long long)(gate * MH + 8 * w + g) * MH + 4 * q;
+                if (F16) {                        // k-step s (16 indices): k-slots 2q, 2q+1 <-> units 16s + 2q (+1), k-slots 2q+8, 2q+9 <-> units 16s + 8 + 2q (+1)
+                    const float* row = W + (long long)(gate * MH + 8 * w + g) * MH + 2 * q;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(row + 16 * c));
-                    split_tf32_fast(v.x, bhi[gate][2 * c][0], blo[gate][2 * c][0]);
-                    split_tf32_fast(v.y, bhi[gate][2 * c][1], blo[gate][2 * c][1]);
-                    split_tf32_fast(v.z, bhi[gate][2 * c + 1][0], blo[gate][2 * c + 1][0]);
-                    split_tf32_fast(v.w, bhi[gate][2 * c + 1][1], blo[gate][2 * c + 1][1]);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const float2 v1 = __ldg(reinterpret_cast<const float2*>(row + 16 * ks));
+                        const float2 v2 = __ldg(reinterpret_cast<const float2*>(row + 16 * ks + 8));
+                        split_f16x2(v1.x, v1.y, bhi[gate][ks][0], blo[gate][ks][0]);
+                        split_f16x2(v2.x, v2.y, bhi[gate][ks][1], blo[gate][ks][1]);
+                    }
+                } else {
+                    const float* row = W + (long long)(gate * MH + 8 * w + g) * MH + 4 * q;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(row + 16 * c));
+                        split_tf32_fast(v.x, bhi[gate][2 * c][0], blo[gate][2 * c][0]);
+                        split_tf32_fast(v.y, bhi[gate][2 * c][1], blo[gate][2 * c][1]);
+                        split_tf32_fast(v.z, bhi[gate][2 * c + 1][0], blo[gate][2 * c + 1][0]);
+                        split_tf32_fast(v.w, bhi[gate][2 * c + 1][1], blo[gate][2 * c + 1][1]);
+                    }
                 }
             }
             cur_head = head;
@@ -646,6 +673,36 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
                     for (int gate = 0; gate < 3; ++gate)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) acc[gate][e] = 0.f;
+                    if (F16) {
+                        // four k-steps of 16: one 128-bit load per operand half; cross terms (scaled by 2^11) in their own accumulators
+                        float accx[3][4];
+#pragma unroll
+                        for (int gate = 0; gate < 3; ++gate)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) accx[gate][e] = 0.f;
+                        uint4 fh[4], fl[4];
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const int o = ((ks * 4 + q) * 8 + (g ^ (q << 1))) * 4;
+                            fh[ks] = *reinterpret_cast<const uint4*>(&hb_hi[o]);
+                            fl[ks] = *reinterpret_cast<const uint4*>(&hb_lo[o]);
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t ahi[4] = {fh[ks].x, fh[ks].y, fh[ks].z, fh[ks].w};
+                            const uint32_t alo[4] = {fl[ks].x, fl[ks].y, fl[ks].z, fl[ks].w};
+#pragma unroll
+                            for (int gate = 0; gate < 3; ++gate) mma_f16(accx[gate], alo, bhi[gate][ks]);
+#pragma unroll
+                            for (int gate = 0; gate < 3; ++gate) mma_f16(accx[gate], ahi, blo[gate][ks]);
+#pragma unroll
+                            for (int gate = 0; gate < 3; ++gate) mma_f16(acc[gate], ahi, bhi[gate][ks]);
+                        }
+#pragma unroll
+                        for (int gate = 0; gate < 3; ++gate)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) acc[gate][e] = fmaf(accx[gate][e], 1.f / 2048.f, acc[gate][e]);
+                    } else {
                     // A fragments in quarters (2 k-steps = 4 x 128-bit loads each), loaded one quarter ahead of the MMAs that use them
                     uint4 fa[2][4];               // [ping-pong][hi k0, hi k1, lo k0, lo k1]
                     auto load_q = [&](int qi, uint4 (&f)[4]) {
@@ -674,6 +731,7 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 #pragma unroll
                             for (int gate = 0; gate < 3; ++gate) mma_tf32(acc[gate], ahi, bhi[gate][ks]);
                         }
+                    }
                     }
 #pragma unroll
                     for (int gate = 0; gate < 3; ++gate)
@@ -720,6 +778,15 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
             }
         };
         auto stage_h = [&](int s, int buf, const float2 (&h)[2]) {     // this thread's h values, split, into the A-operand tile
+            if (F16) {                            // unit pair 4w + q = k-step w/2, fragment half w%2, quad lane q: {row g, row g+8} as two half2
+                uint32_t hi[2], lo[2];
+                split_f16x2(h[0].x, h[0].y, hi[0], lo[0]);
+                split_f16x2(h[1].x, h[1].y, hi[1], lo[1]);
+                const int o = (((w >> 1) * 4 + q) * 8 + (g ^ (q << 1))) * 4 + (w & 1) * 2;
+                *reinterpret_cast<uint2*>(&sm.st[s].hbuf[buf][0][o]) = make_uint2(hi[0], hi[1]);
+                *reinterpret_cast<uint2*>(&sm.st[s].hbuf[buf][1][o]) = make_uint2(lo[0], lo[1]);
+                return;
+            }
             uint32_t hi[4], lo[4];
             split_tf32_fast(h[0].x, hi[0], lo[0]); split_tf32_fast(h[1].x, hi[1], lo[1]);
             split_tf32_fast(h[0].y, hi[2], lo[2]); split_tf32_fast(h[1].y, hi[3], lo[3]);
@@ -1312,7 +1379,8 @@ extern "C" int crvae_gru_fwd_mma(float* gates, const float* b_ih, const float* w
     const int smem = (int)sizeof(FwdPipeSmem);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gru_fwd_mma_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gru_fwd_mma_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gru_fwd_mma_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { set_error("gru_fwd_mma_ws smem attr (%d B): %s", smem, cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
@@ -1328,7 +1396,10 @@ extern "C" int crvae_gru_fwd_mma(float* gates, const float* b_ih, const float* w
         if ((rc = make_tmap_generic(&tH, hs, 4, dh, sh, bh, false))) return rc;
         if ((rc = make_tmap_generic(&tN, ghn, 4, dh, sh, bh, false))) return rc;
     }
-    gru_fwd_mma_ws_kernel<<<grid, WS_THREADS, smem, (cudaStream_t)stream>>>(tG, tH, tN, a, pf, npph);
+    // operand format of the gate product: fp16 hi | lo (m16n8k16, 36 MMAs per warp-step) unless CRVAE_MMA_F16=0 (tf32 hi | lo, 72)
+    static const int f16 = [] { const char* e = getenv("CRVAE_MMA_F16"); return e ? atoi(e) : 1; }();
+    if (f16) gru_fwd_mma_ws_kernel<true><<<grid, WS_THREADS, smem, (cudaStream_t)stream>>>(tG, tH, tN, a, pf, npph);
+    else     gru_fwd_mma_ws_kernel<false><<<grid, WS_THREADS, smem, (cudaStream_t)stream>>>(tG, tH, tN, a, pf, npph);
     return check_launch("gru_fwd_mma_ws_kernel");
 }
 
