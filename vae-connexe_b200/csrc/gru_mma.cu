@@ -607,6 +607,7 @@ gru_fwd_mma_ws_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         if (++p.t == T) p = pos_of_pair(p.j + 1, s);
     };
 
+    if (tid == 32) { prefetch_tmap(&tmG); prefetch_tmap(&tmH); prefetch_tmap(&tmN); }
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -1028,6 +1029,7 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
         if (--p.t < 0) p = pos_of_pair(p.j + 1, s);
     };
 
+    if (tid == 32) { prefetch_tmap(&tm.g); prefetch_tmap(&tm.n); prefetch_tmap(&tm.h); prefetch_tmap(&tm.z); if (HAS_DHS) prefetch_tmap(&tm.d); }
     if (tid == 0) {
         for (int s = 0; s < pf; ++s) {
 #pragma unroll
