@@ -187,11 +187,15 @@ int crvae_gru_bwd_ll(float* gates, float* ghn, const float* hs, const float* h0,
                      const float* w_hh, const float* w_lin, const float* dpred, const float* dh_last,
                      const float* dhs, float* db_hh, float* db_ih, float* dw_lin, float* db_lin, float* dh0,
                      int P, int T, int B, void* workspace, void* stream);
-/* Register-resident tensor-core forms of the two calls above (warp-level mma.sync m16n8k8, 3xTF32; same arguments,
- * buffers and in-place conventions; results agree with the exact kernels to ~1e-6 relative, like the *_tc kernels).
- * One CTA per (head, 16-row tile) in a persistent grid; W_hh is held in registers as pre-split tf32 B fragments, the
- * accumulators land in the registers of the thread that does the gate math, one __syncthreads per step.  The default
- * recurrent path of every shape (decoder heads, head shards, the encoder, VRAE4E, VRAE.py).                          */
+/* Warp-level tensor-core forms of the two calls above (mma.sync; same arguments, buffers and in-place conventions; results
+ * agree with the exact kernels to ~2e-6, like the *_tc kernels).  Warp-specialised: 8 MMA warps hold W_hh in registers as
+ * pre-split B fragments, 8 gate-math warps do the cell math and the staging; (head, 16-row tile)s in a persistent grid, two
+ * tiles of a head per CTA once there are more tiles than SMs; every global access is a TMA tile copy (4-D tensor maps over
+ * gates / hs / ghn / h0 / dhs, rows past B clipped).  Forward: fp16 hi|lo operands on m16n8k16 (tf32 hi|lo with
+ * CRVAE_MMA_F16=0); BPTT: tf32 hi|lo, product split over K, partial products summed in fixed order (deterministic).
+ * The default recurrent path of the shapes bound by the latency of one step: head shards up to 26 heads, the encoder,
+ * VRAE4E, VRAE.py (vae-connexe_b200/rec.py); the BPTT also of p = 100 on one rank when run as one launch.
+ * All row pointers 16-byte aligned; `workspace` >= crvae_gru_bwd_workspace(P, B).                                       */
 int crvae_gru_fwd_mma(float* gates, const float* b_ih, const float* w_hh, const float* b_hh,
                       const float* h0, int64_t h0_head_stride, const float* w_lin, const float* b_lin,
                       float* hs, float* ghn, float* pred, int P, int T, int B, int t_skip, void* stream);
