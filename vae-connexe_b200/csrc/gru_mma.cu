@@ -1259,7 +1259,7 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
                     float* slab = st.slab[slot];
                     float* gns = st.gn[slot];
                     const float* hps = st.hp[slot];
-                    float fr[4], fz[4], fn_[4];
+                    float fr[4], fz[4], fn_[4], fa[4];         // da_r, da_z, da_n*r (the MMA operand) and da_n of the 4 elements
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const float2 r2 = *reinterpret_cast<const float2*>(slab + o_r[i]), z2 = *reinterpret_cast<const float2*>(slab + o_z[i]),
@@ -1288,15 +1288,15 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
                         }
                         if (w == 0 && q == 0) sums[s][10] += dp[i];
                         hcur[s][i] = p2;
-                        *reinterpret_cast<float2*>(slab + o_r[i]) = make_float2(dar[0], dar[1]);
-                        *reinterpret_cast<float2*>(slab + o_z[i]) = make_float2(daz[0], daz[1]);
-                        *reinterpret_cast<float2*>(slab + o_n[i]) = make_float2(dan[0], dan[1]);
-                        *reinterpret_cast<float2*>(gns + o_h[i]) = make_float2(dgn[0], dgn[1]);
                         fr[i] = dar[0]; fr[2 + i] = dar[1];
                         fz[i] = daz[0]; fz[2 + i] = daz[1];
                         fn_[i] = dgn[0]; fn_[2 + i] = dgn[1];
+                        fa[i] = dan[0]; fa[2 + i] = dan[1];
                     }
-                    // the partner lane's A fragments {x[g][u], x[g+8][u], x[g][u+1], x[g+8][u+1]} of the three gate blocks, split hi | lo
+                    // the MMA operand first -- the partner lane's A fragments {x[g][u], x[g+8][u], x[g][u+1], x[g+8][u+1]} of the three gate
+                    // blocks, split hi | lo -- it is all the M warps wait for; dgi / dgh_n are staged after they are released (measured:
+                    // 193.5 -> 187.4 us at P = 100; the same reordering in the forward, whose gate-math warps are the bottleneck, costs
+                    // more in the second barrier than it gains: 160 -> 172 us)
                     {
                         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -1312,15 +1312,23 @@ gru_bwd_mma_ws_kernel(const __grid_constant__ BwdTmaps tm, GruMmaBwdArgs a, int 
                         *reinterpret_cast<uint4*>(&st.dghb[w][2][0][lane * 4]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4*>(&st.dghb[w][2][1][lane * 4]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                    fence_proxy_async_smem();
                     pending[s] = true;
                     ppos[s] = pp;
+                    p_warps_sync();               // every P warp has read the previous partials and staged its operand: M may overwrite accb
+                    if (ptid == 0) mbar_arrive(&st.dgh_ready);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        *reinterpret_cast<float2*>(slab + o_r[i]) = make_float2(fr[i], fr[2 + i]);
+                        *reinterpret_cast<float2*>(slab + o_z[i]) = make_float2(fz[i], fz[2 + i]);
+                        *reinterpret_cast<float2*>(slab + o_n[i]) = make_float2(fa[i], fa[2 + i]);
+                        *reinterpret_cast<float2*>(gns + o_h[i]) = make_float2(fn_[i], fn_[2 + i]);
+                    }
+                    fence_proxy_async_smem();
+                } else {
+                    p_warps_sync();
                 }
-                p_warps_sync();                   // every P warp has read the previous partials and staged its operand: M may overwrite accb
-                if (ptid == 0) {
-                    if (pp.vrows > 0) mbar_arrive(&st.dgh_ready);
-                    plumb(s, n, pp);
-                }
+                p_warps_sync();                   // every P warp has staged dgi / dgh_n of step n
+                if (ptid == 0) plumb(s, n, pp);
                 pos[s] = nx;
             }
         }
