@@ -57,9 +57,14 @@ __global__ void __launch_bounds__(DZ_THREADS) dz_allreduce_latent_bwd_kernel(DzA
     // 1. local sum over this rank's heads, fixed order
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live)
-        for (int i = 0; i < a.P; ++i) {
-            const float4 v = __ldcs(reinterpret_cast<const float4*>(a.dh0 + (long long)i * a.n + e0));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        for (int i0 = 0; i0 < a.P; i0 += 8) {                 // 8 loads in flight, then the adds in head order
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = i0 + j < a.P ? __ldcs(reinterpret_cast<const float4*>(a.dh0 + (long long)(i0 + j) * a.n + e0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (i0 + j < a.P) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
         }
     if (live) *reinterpret_cast<float4*>(mine + slot_off + e0) = acc;
     __threadfence_system();
@@ -76,12 +81,26 @@ __global__ void __launch_bounds__(DZ_THREADS) dz_allreduce_latent_bwd_kernel(DzA
     }
     __syncthreads();
     // 4. gather the partials over NVLink, summed in rank order (identical on every rank)
+    // (all peer loads are issued before the first add: eight NVLink round trips in flight instead of one after the other)
     float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live)
-        for (int r = 0; r < a.world; ++r) {
-            const float4 v = ld_volatile_f4(a.peers[r] + slot_off + e0);
-            dz.x += v.x; dz.y += v.y; dz.z += v.z; dz.w += v.w;
+    if (live) {
+        // (unconditional loads -- ranks past `world` re-read this rank's own slot -- so that nothing but the loads stands between them)
+#pragma unroll
+        for (int half = 0; half < DZ_MAX_WORLD; half += 8) {
+            if (half >= a.world) break;
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = half + j;
+                v[j] = ld_volatile_f4((r < a.world ? a.peers[r] : mine) + slot_off + e0);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool on = half + j < a.world;
+                dz.x += on ? v[j].x : 0.f; dz.y += on ? v[j].y : 0.f; dz.z += on ? v[j].z : 0.f; dz.w += on ? v[j].w : 0.f;
+            }
         }
+    }
     if (tid == 0) my_epoch[c] = e;
     if (!live) return;
     if (a.dz_out) *reinterpret_cast<float4*>(a.dz_out + e0) = dz;
