@@ -455,3 +455,30 @@ def test_driver_phase_handoff_wire_format(cpu_backend, traj, tmp_path):
     assert np.array_equal(out2["GC_est"], ref_gc) and out2["loss_phase2"] is not None
     with pytest.raises(ValueError):
         driver.load_gc(str(tmp_path / driver.GC_FILE), p=7)
+
+
+def test_recurrent_kernel_selection_rules():
+    """rec.py: which recurrent implementation a (heads, batch) shape gets -- MMA forward up to MMA_MAX_HEADS heads, MMA BPTT
+    up to MMA_BWD_MAX_TILES 16-row tiles, and the fallbacks when a family is switched off or missing from the backend."""
+    import importlib
+    import types
+    from vae_connexe_b200 import rec as R
+    full = types.SimpleNamespace(gru_fwd_mma=1, gru_bwd_mma=1, gru_fwd_ll=1, gru_bwd_ll=1, gru_dwhh_tc=1)
+    no_mma = types.SimpleNamespace(gru_fwd_ll=1, gru_bwd_ll=1)
+    assert R.has_mma(full) and not R.has_mma(no_mma) and R.has_ll(no_mma)
+    assert R.mma_preferred(1) and R.mma_preferred(R.MMA_MAX_HEADS) and not R.mma_preferred(R.MMA_MAX_HEADS + 1)
+    assert R.mma_bwd_preferred(full, 100, 256) and not R.mma_bwd_preferred(full, 1000, 256)      # 1,600 / 16,000 tiles
+    assert not R.mma_bwd_preferred(no_mma, 1, 256)
+    os_env = dict(CRVAE_MMA="0")
+    import os
+    old = os.environ.get("CRVAE_MMA")
+    try:
+        os.environ.update(os_env)
+        R0 = importlib.reload(R)
+        assert not R0.has_mma(full) and not R0.mma_bwd_preferred(full, 13, 256)
+    finally:
+        if old is None:
+            os.environ.pop("CRVAE_MMA", None)
+        else:
+            os.environ["CRVAE_MMA"] = old
+        importlib.reload(R)
