@@ -556,9 +556,22 @@ class CRVAEEngine:
         k.latent_head_fwd(self.enc_hs[0, ENC_STEPS - 1], th["lat_w"], th["lat_b"], self.eps, self.lat, self.zlat, self.kl, B,
                           self.kl_form, self.ws_lat)
 
-    def _enc_backward_chain(self, beta):
+    def _enc_backward_chain(self, beta, stage_eps: bool = False):
+        """stage_eps: copy the next iteration's noise into place on the auxiliary stream as soon as the last reader of the current
+        noise (the dz / latent backward) is done, instead of on the critical path in front of the encoder forward; returns the
+        event to wait for (None: not staged)."""
         k, th, g, B, P, p_ = self.k, self.theta, self.grad, self.B, self.P, self.p
         self._dz_latent_bwd(beta)
+        ev_eps = None
+        if stage_eps and self.device.type == "cuda" and self.use_side_stream:
+            cur = torch.cuda.current_stream()
+            if getattr(self, "_aux", None) is None:
+                self._aux = torch.cuda.Stream(device=self.device, priority=-1)
+            ev = torch.cuda.Event(); ev.record(cur)
+            self._aux.wait_event(ev)
+            with torch.cuda.stream(self._aux):
+                self.eps.copy_(self.eps_next)
+                ev_eps = torch.cuda.Event(); ev_eps.record(self._aux)
         k.latent_head_bwd(self.dlat, self.enc_hs[0, ENC_STEPS - 1], th["lat_w"], g["lat_w"], g["lat_b"], self.dhT, B)
         dwhh = R.gru_backward_small(k, self.enc_gates, self.enc_ghn, self.enc_hs, self.h0_zero, 0, th["enc_w_hh"], None, None, self.dhT,
                                     None, g["enc_w_hh"].view(1, G, H), g["enc_b_hh"], g["enc_b_ih"], None, None, self.enc_dh0,
@@ -581,6 +594,7 @@ class CRVAEEngine:
             k.proj_wgrad(self.enc_gates, self.enc_in, None, g["enc_w_ih"], 1, ENC_STEPS, B, p_, 0, self.ws_wgrad)
         if ev_aux is not None:
             torch.cuda.current_stream().wait_event(ev_aux)
+        return ev_eps
 
     def flow_pre(self):
         """pre: encoder chain on the staged noise (eps_next) + every head's projection, for the CURRENT weights."""
@@ -641,7 +655,7 @@ class CRVAEEngine:
             k.dot_small(self.sse, self.P, 1.0 / (DEC_STEPS * self.B), self.loss)       # loss of the forward just completed
             for e in ev_bwd:
                 side.wait_event(e)
-            self._enc_backward_chain(beta)
+            ev_eps = self._enc_backward_chain(beta, stage_eps=with_pre)
         for gi_, ((lo, hi), st) in enumerate(zip(fl["groups"], fl["streams"])):
             ctx = torch.cuda.stream(st) if st is not None else self._on(None)
             with ctx:
@@ -655,7 +669,10 @@ class CRVAEEngine:
                 side.wait_event(e)
             self._flow_gd_rest(lr)
             if with_pre:
-                self.eps.copy_(self.eps_next)
+                if ev_eps is None:
+                    self.eps.copy_(self.eps_next)
+                else:
+                    side.wait_event(ev_eps)
                 self._enc_forward_chain()
             e_side = torch.cuda.Event(); e_side.record(side)
         for e in ev_done:
