@@ -482,3 +482,32 @@ def test_recurrent_kernel_selection_rules():
         else:
             os.environ["CRVAE_MMA"] = old
         importlib.reload(R)
+
+
+def test_mma_kernel_shared_memory_layouts():
+    """The two shared-memory index maps of csrc/gru_mma.cu, restated: frag_idx (A operand in MMA-fragment order) is a bijection and
+    the 8 lanes of a quarter warp hit 8 different 16-byte bank groups on the consumer side; sw_idx (TMA SWIZZLE_128B tile) is a
+    bijection and the 16 lanes of a half warp (4 row groups x 4 quad lanes, 64-bit accesses) cover all 32 banks exactly once."""
+    def frag_idx(p, g):
+        return (p * 8 + (g ^ (((p >> 1) & 3) << 1))) * 4
+
+    def sw_idx(C, row, col):
+        line, unit = row * C + (col >> 5), (col & 31) >> 2
+        return line * 32 + (((unit ^ (line & 7)) << 2) | (col & 3))
+
+    for npairs in (32, 96):                       # forward (64 units) / BPTT (192 reduction indices)
+        idx = sorted(frag_idx(p, g) for p in range(npairs) for g in range(8))
+        assert idx == list(range(0, npairs * 8 * 4, 4))
+        for ks in range(npairs // 4):             # consumer: k-step ks, lane (g, q) reads pair 8*(ks/2) + 2q + ks%2
+            for g0 in (0, 2, 4, 6):               # a quarter warp = row groups g0, g0+1 x quad lanes 0..3
+                groups = {(frag_idx(8 * (ks >> 1) + 2 * q + (ks & 1), g) // 4) % 8 for g in (g0, g0 + 1) for q in range(4)}
+                assert len(groups) == 8
+    for C in (6, 2):                              # gate slab (192 columns) / h, gh_n tiles (64 columns)
+        idx = sorted(sw_idx(C, r, c) for r in range(16) for c in range(32 * C))
+        assert idx == list(range(16 * 32 * C))
+        for w in range(8):
+            for gate in range(C // 2):
+                for g0 in (0, 4):                 # half warp: row groups g0..g0+3, quad lanes 0..3, two consecutive floats each
+                    banks = [sw_idx(C, g + 8 * i, gate * 64 + 8 * w + 2 * q + e) % 32 for i in (0,) for g in range(g0, g0 + 4)
+                             for q in range(4) for e in (0, 1)]
+                    assert sorted(banks) == list(range(32))
